@@ -1,0 +1,144 @@
+/*
+ * omr_b200.h — C ABI of libomr_b200.so: the B200 (sm_100a) implementation of InstantOMR's detection hot path.
+ *
+ * Drop-in boundary.  The reference (xiangxiecrypto/tfhe-omr, crate omr_core) has no FFI; the boundary is the
+ * Rust public API of `Detector` (omr_core/src/lib.rs:21-31).  Each entry point below names the reference
+ * interface it replaces.  All buffers are flat, little-endian, caller-owned; every call returns an omr_status
+ * and never unwinds.  There is NO CPU fallback: without a CUDA device every compute call fails with
+ * OMR_ERR_CUDA.
+ *
+ * Layout conventions (Primus-fhe's own in-memory layouts are not available — "parity
+ * unpinned" — so the shim flattens into these):
+ *   negacyclic NTT: forward = Cooley-Tukey, natural order in, bit-reversed order out, out[k] = a(psi^(2*brv(k)+1)),
+ *     psi1 = 4073518 (mod q1 = 134215681, N1 = 1024), psi2 = 765727830662934 (mod q2 = 1125899906826241, N2 = 2048).
+ *   RLWE (a, b): b = a*s + m + e.   RGSW rows: [0,L) = RLWE(-s*m*g_j), [L,2L) = RLWE(m*g_j), g_j = 2^(drop + w*j).
+ */
+#ifndef OMR_B200_H
+#define OMR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMR_CLUE_N 512        /* clue LWE dimension            parameters/mod.rs:41 */
+#define OMR_CLUE_COUNT 7      /* clues per message             parameters/mod.rs:48 */
+#define OMR_N1 1024           /* first-level ring dimension    parameters/mod.rs:51 */
+#define OMR_Q1 134215681u     /* FirstLevelField               parameters/mod.rs:18 */
+#define OMR_LWE2_N 670        /* intermediate LWE dimension    parameters/mod.rs:69 */
+#define OMR_N2 2048           /* second-level ring dimension   parameters/mod.rs:77 */
+#define OMR_Q2 1125899906826241ull /* SecondLevelField         parameters/mod.rs:21 */
+#define OMR_P 257             /* output plain modulus          parameters/mod.rs:93 */
+#define OMR_PAYLOAD_LEN 612   /* payload.rs:8 */
+#define OMR_PV_WORDS (2 * OMR_N2) /* one pertinency ciphertext = NttRlweCiphertext<SecondLevelField> */
+
+typedef enum {
+    OMR_OK = 0,
+    OMR_ERR_INVALID = 1,   /* bad argument (the reference panics/asserts: detector.rs:236,511) */
+    OMR_ERR_CUDA = 2,      /* CUDA runtime failure or no device — never falls back to the CPU */
+    OMR_ERR_ALLOC = 3,
+    OMR_ERR_STATE = 4      /* call order (e.g. encode before any detect) */
+} omr_status;
+
+/* key-blob flags */
+#define OMR_KEYS_NTT_NATIVE 0u /* ring polynomials already in this library's NTT convention (above) */
+#define OMR_KEYS_COEFF 1u      /* ring polynomials in coefficient form; transformed on upload (Rust-shim path) */
+
+/* Replaces DetectionKey (omr_core/src/key_gen/detection.rs:9-16) flattened:
+ *   BlindRotationKey<F1> -> bsk1, NonPowOf2LweKeySwitchingKey -> ksk, BlindRotationKey<F2> -> bsk2,
+ *   TraceKey<F2> -> trace.  N2^-1 and both LUTs (detector.rs:457-503) are derived inside. */
+typedef struct {
+    const uint32_t* bsk1;  /* [512][8][2][1024]   mod q1 */
+    const uint32_t* ksk;   /* [1024][27][671]     mod q1, (a[670], b) */
+    const uint64_t* bsk2;  /* [670][12][2][2048]  mod q2 */
+    const uint64_t* trace; /* [11][25][2][2048]   mod q2, step t <-> automorphism X -> X^(2^(11-t)+1) */
+    uint32_t flags;
+} omr_key_blobs;
+
+/* Replaces DetectTimeInfoPerMessage / DetectTimeInfo (detector.rs:43-57): device time per stage, milliseconds,
+ * summed over the batch of the call. */
+typedef struct {
+    float detect_ms;
+    float first_level_bootstrapping_ms;  /* L1 blind rotations + key switch + modulus switch */
+    float second_level_bootstrapping_ms;
+    float trace_ms;
+} omr_stage_times;
+
+/* Replaces RetrievalParams<F> (parameters/retrieval_params.rs:11-46); fill with omr_retrieval_params_init. */
+typedef struct {
+    uint64_t index_modulus;
+    uint32_t polynomial_size, bucket_count_per_segment, slots_per_bucket, slots_per_segment, segment_count,
+        segment_per_cipher, max_encode_indices_cipher_count, pertinent_count, combination_count, cmb_count_per_cipher;
+    uint64_t all_payloads_count;
+} omr_retrieval_params;
+
+typedef struct omr_ctx omr_ctx;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------- */
+/* Replaces Detector::new(DetectionKey) (detector.rs:85-110): uploads and owns device copies of the keys. */
+int omr_ctx_create(int device, const omr_key_blobs* keys, omr_ctx** out);
+/* Keys already resident on `device` (same layouts); copied once more into the context's internal form. */
+int omr_ctx_create_device_keys(int device, const omr_key_blobs* device_keys, omr_ctx** out);
+void omr_ctx_destroy(omr_ctx* ctx);
+const char* omr_last_error(const omr_ctx* ctx); /* NULL ctx -> error of the last failed create */
+/* Detector::detect_key_size (detector.rs:112-114): bytes of key material resident on the device */
+size_t omr_detect_key_size(const omr_ctx* ctx);
+/* RetrievalParams::new(257, 2048, D, k, 130, 25, 2) — secret.rs:189-209 */
+int omr_retrieval_params_init(uint64_t all_payloads_count, uint32_t pertinent_count, omr_retrieval_params* out);
+
+/* ---- the hot path, host buffers (what the Rust shim binds) ---------------------------------------------------- */
+/* Replaces `clues_list.par_iter().map(|c| detector.detect(c))` (examples/omr.rs:160-164 over detector.rs:135-166)
+ * for B messages.  clue_a [B][512], clue_b [B][7] (CmLweCiphertext<u16> flattened).  The B pertinency ciphertexts
+ * are kept in the context's device-resident pertinency store at positions [global_index0, global_index0+B)
+ * (the store grows on demand) and, when pv_out != NULL, also copied to the host as [B][2][2048].
+ * times may be NULL (detect_with_time_info, detector.rs:169-221). */
+int omr_detect_batch(omr_ctx* ctx, const uint16_t* clue_a, const uint16_t* clue_b, size_t B, uint64_t global_index0,
+                     uint64_t* pv_out, omr_stage_times* times);
+/* Forget the pertinency store (start a new bulletin board). */
+int omr_pv_reset(omr_ctx* ctx);
+/* Replaces Detector::encode_pertinent_indices (detector.rs:223-339) over the resident pertinency store, for
+ * ciphertexts [cipher_idx0, cipher_idx0+n_cipher).  The reference draws buckets from thread_rng (detector.rs:262);
+ * here they are a counter hash of (seed, cipher, global message index, segment), see DESIGN.md.
+ * out [n_cipher][2][2048] receives this context's PARTIAL digest already reduced mod q2. */
+int omr_encode_indices(omr_ctx* ctx, const omr_retrieval_params* rp, uint64_t seed, uint32_t cipher_idx0,
+                       uint32_t n_cipher, uint64_t* out);
+/* Replaces Detector::encode_pertinent_payloads (detector.rs:341-453).  payloads [count][612] for the messages in
+ * the store (count must equal the store size, global indices index0..), weights [rows][weight_stride] row-major
+ * u16 in [0,257) with column = GLOBAL message index (the caller draws them: StdRng + Uniform, detector.rs:376-387),
+ * rows >= n_cipher*cmb_per_cipher.  out [n_cipher][2][2048]. */
+int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, const uint16_t* weights,
+                        size_t weight_stride, uint32_t n_cipher, uint32_t cmb_per_cipher, uint64_t* out);
+
+/* ---- device-pointer forms (inputs already in HBM; `stream` is a cudaStream_t, NULL = the default stream) -------------------------- */
+int omr_detect_batch_device(omr_ctx* ctx, const uint16_t* d_clue_a, const uint16_t* d_clue_b, size_t B,
+                            uint64_t* d_pv /*[B][2][2048]*/, void* stream, omr_stage_times* times);
+int omr_encode_indices_device(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* d_pv, size_t count,
+                              uint64_t index0, uint64_t seed, uint32_t cipher_idx0, uint32_t n_cipher,
+                              uint64_t* d_out, void* stream);
+int omr_encode_payloads_device(omr_ctx* ctx, const uint64_t* d_pv, const uint16_t* d_payloads, size_t count,
+                               uint64_t index0, const uint16_t* d_weights, size_t weight_stride, uint32_t n_cipher,
+                               uint32_t cmb_per_cipher, uint64_t* d_out, void* stream);
+/* After a cross-GPU integer sum of partial digests (rayon reduce + add_element_wise, detector.rs:333-336,445-448):
+ * reduce every word mod q2 in place (inputs < 2^63). */
+int omr_digest_reduce_mod(omr_ctx* ctx, uint64_t* d_words, size_t n_words, void* stream);
+
+/* ---- stage entry points (device pointers) — the stage list of benches/two_level_bs.rs:47-145 ------------------- */
+int omr_l1_blind_rotate_device(omr_ctx* ctx, const uint16_t* d_clue_a, const uint16_t* d_clue_b, size_t B,
+                               uint32_t* d_rlwe /*[B][2][1024] sum of the 7 accumulators*/, void* stream);
+int omr_keyswitch_device(omr_ctx* ctx, const uint32_t* d_rlwe /*[B][2][1024]*/, size_t B,
+                         uint32_t* d_lwe /*[B][671] mod 4096, offset added*/, void* stream);
+int omr_l2_blind_rotate_device(omr_ctx* ctx, const uint32_t* d_lwe /*[B][671]*/, size_t B,
+                               uint64_t* d_rlwe /*[B][2][2048]*/, void* stream);
+int omr_trace_device(omr_ctx* ctx, uint64_t* d_rlwe /*[B][2][2048], in place -> NttRlwe*/, size_t B, void* stream);
+/* batched negacyclic NTTs, in place, canonical outputs; level 1: u32 [batch][1024], level 2: u64 [batch][2048] */
+int omr_ntt_forward_device(omr_ctx* ctx, int level, void* d_data, size_t batch, void* stream);
+int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d_data, size_t batch, void* stream);
+
+/* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
+uint64_t omr_launch_count(const omr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMR_B200_H */

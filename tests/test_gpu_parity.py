@@ -1,0 +1,96 @@
+"""GPU parity tests: every stage of the CUDA path against the CPU oracle on the same inputs, bit-exact, through the
+C ABI (libomr_b200.so).  Run on the B200 box with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x, dtype):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x).view(dtype)).cuda()
+
+
+def _mixed_clues(keypack, decoy, n, pertinent_idx, seed=11):
+    a, b = decoy.gen_clues(seed, n)
+    for i in pertinent_idx:
+        ai, bi = keypack.gen_clues(seed + 1, 1, index0=i)
+        a[i], b[i] = ai[0], bi[0]
+    return a, b
+
+
+def test_ntt_forward_inverse_vs_oracle(detector):
+    import torch
+    rng = np.random.default_rng(1)
+    x1 = rng.integers(0, O.Q1, (5, O.N1), dtype=np.uint32)
+    x2 = rng.integers(0, O.Q2, (5, O.N2), dtype=np.uint64)
+    for level, x, dt, fwd, inv in ((1, x1, np.int32, "orc_ntt1_forward", "orc_ntt1_inverse"), (2, x2, np.int64, "orc_ntt2_forward", "orc_ntt2_inverse")):
+        ref = x.copy(); getattr(O.lib(), fwd)(O.ptr(ref), ref.shape[0])
+        d = _dev(x, dt)
+        detector.ntt(level, d); torch.cuda.synchronize()
+        got = d.cpu().numpy().view(x.dtype)
+        assert np.array_equal(got, ref)
+        detector.ntt(level, d, inverse=True); torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy().view(x.dtype), x)
+
+
+def test_stages_bit_exact(detector, keypack, decoy):
+    import torch
+    a, b = _mixed_clues(keypack, decoy, 3, [1])
+    da, db = _dev(a, np.int16), _dev(b, np.int16)
+    l1 = detector.first_level_blind_rotate(da, db); torch.cuda.synchronize()
+    ref_l1 = keypack.l1(a, b)
+    assert np.array_equal(l1.cpu().numpy().view(np.uint32), ref_l1)
+    ks = detector.key_switch(l1); torch.cuda.synchronize()
+    ref_ks = keypack.keyswitch(ref_l1)
+    assert np.array_equal(ks.cpu().numpy().view(np.uint32), ref_ks)
+    l2 = detector.second_level_blind_rotate(ks); torch.cuda.synchronize()
+    ref_l2 = keypack.l2(ref_ks)
+    assert np.array_equal(l2.cpu().numpy().view(np.uint64), ref_l2)
+    tr = detector.trace(l2.clone()); torch.cuda.synchronize()
+    ref_tr = keypack.trace(ref_l2)
+    assert np.array_equal(tr.cpu().numpy().view(np.uint64), ref_tr)
+    # whole pipeline in one call
+    pv = detector.detect((a, b))
+    assert np.array_equal(pv.to_host(), ref_tr)
+
+
+def test_omd_acceptance(detector, keypack, decoy):
+    """omr_core/examples/omd.rs:45-58: pertinent -> [1,0,...,0], non-pertinent -> all 0."""
+    a, b = _mixed_clues(keypack, decoy, 2, [0], seed=21)
+    pv = detector.detect((a, b)).to_host()
+    d0, d1 = keypack.decrypt_decode(pv[0]), keypack.decrypt_decode(pv[1])
+    assert d0[0] == 1 and not d0[1:].any()
+    assert not d1.any()
+
+
+def test_digest_bit_exact_and_decode(detector, keypack, decoy):
+    """examples/omr.rs / omr_time_analyze2.rs:220-240 at D = 48: digest bit-exact vs oracle packing of the same
+    pertinency vector, and the decoded set / payloads equal the planted ones."""
+    import tfhe_omr_b200 as omr
+    D, pert = 48, [3, 17, 40]
+    a, b = _mixed_clues(keypack, decoy, D, pert, seed=31)
+    pv = detector.detect((a, b))
+    pvh = pv.to_host()
+    rng = np.random.default_rng(5)
+    payloads = rng.integers(0, 256, (D, O.PAYLOAD_LEN), dtype=np.uint16)
+    rp = omr.RetrievalParams(D, len(pert))
+    ref_rp = O.retrieval_params(D, len(pert))
+    assert rp.max_encode_indices_cipher_count == ref_rp["max_encode_indices_cipher_count"]
+    ncomb = rp.combination_count
+    nciph = rp.payload_cipher_count
+    weights = np.zeros((nciph * 2, D), np.uint16)
+    weights[:ncomb] = O.chacha12_weights(bytes(range(32)), ncomb * D).reshape(ncomb, D)
+    seed = 0xABCDEF
+    idx = detector.encode_pertinent_indices(rp, pv, seed=seed, cipher_index=0, n_cipher=rp.max_encode_indices_cipher_count)
+    pay = detector.encode_pertinent_payloads(pv, payloads, ncomb, 2, weights)
+    idx_h = idx.cpu().numpy().view(np.uint64); pay_h = pay.cpu().numpy().view(np.uint64)
+    for c in range(rp.max_encode_indices_cipher_count):
+        assert np.array_equal(idx_h[c], O.encode_indices(D, len(pert), pvh, 0, seed, c))
+    assert np.array_equal(pay_h, O.encode_payloads(pvh, payloads, 0, weights, nciph))
+    st, found, solved = keypack.decode_digest(D, len(pert), idx_h, pay_h, weights)
+    assert st == 0 and list(found) == pert
+    for i, p in zip(found, solved):
+        assert np.array_equal(p, payloads[i])

@@ -1,0 +1,75 @@
+"""ctypes binding of libomr_b200.so (include/omr_b200.h).  Fails loudly when the CUDA library is missing: there is
+no CPU path in this package."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libomr_b200.so")
+
+OMR_OK, OMR_ERR_INVALID, OMR_ERR_CUDA, OMR_ERR_ALLOC, OMR_ERR_STATE = range(5)
+KEYS_NTT_NATIVE, KEYS_COEFF = 0, 1
+
+# every symbol include/omr_b200.h declares (tests check the library exports each of them)
+EXPORTS = [
+    "omr_ctx_create", "omr_ctx_create_device_keys", "omr_ctx_destroy", "omr_last_error", "omr_detect_key_size",
+    "omr_retrieval_params_init", "omr_detect_batch", "omr_pv_reset", "omr_encode_indices", "omr_encode_payloads",
+    "omr_detect_batch_device", "omr_encode_indices_device", "omr_encode_payloads_device", "omr_digest_reduce_mod",
+    "omr_l1_blind_rotate_device", "omr_keyswitch_device", "omr_l2_blind_rotate_device", "omr_trace_device",
+    "omr_ntt_forward_device", "omr_ntt_inverse_device", "omr_launch_count",
+]
+
+
+class KeyBlobs(C.Structure):
+    _fields_ = [("bsk1", C.c_void_p), ("ksk", C.c_void_p), ("bsk2", C.c_void_p), ("trace", C.c_void_p), ("flags", C.c_uint32)]
+
+
+class StageTimes(C.Structure):
+    _fields_ = [("detect_ms", C.c_float), ("first_level_bootstrapping_ms", C.c_float),
+                ("second_level_bootstrapping_ms", C.c_float), ("trace_ms", C.c_float)]
+
+
+class RetrievalParamsC(C.Structure):
+    _fields_ = [("index_modulus", C.c_uint64)] + [(n, C.c_uint32) for n in (
+        "polynomial_size", "bucket_count_per_segment", "slots_per_bucket", "slots_per_segment", "segment_count",
+        "segment_per_cipher", "max_encode_indices_cipher_count", "pertinent_count", "combination_count",
+        "cmb_count_per_cipher")] + [("all_payloads_count", C.c_uint64)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(tfhe_omr_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32, sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
+    P = C.POINTER
+    L.omr_ctx_create.restype = i32; L.omr_ctx_create.argtypes = [i32, P(KeyBlobs), P(vp)]
+    L.omr_ctx_create_device_keys.restype = i32; L.omr_ctx_create_device_keys.argtypes = [i32, P(KeyBlobs), P(vp)]
+    L.omr_ctx_destroy.restype = None; L.omr_ctx_destroy.argtypes = [vp]
+    L.omr_last_error.restype = C.c_char_p; L.omr_last_error.argtypes = [vp]
+    L.omr_detect_key_size.restype = sz; L.omr_detect_key_size.argtypes = [vp]
+    L.omr_launch_count.restype = u64; L.omr_launch_count.argtypes = [vp]
+    L.omr_retrieval_params_init.restype = i32; L.omr_retrieval_params_init.argtypes = [u64, u32, P(RetrievalParamsC)]
+    L.omr_detect_batch.restype = i32; L.omr_detect_batch.argtypes = [vp, vp, vp, sz, u64, vp, P(StageTimes)]
+    L.omr_pv_reset.restype = i32; L.omr_pv_reset.argtypes = [vp]
+    L.omr_encode_indices.restype = i32; L.omr_encode_indices.argtypes = [vp, P(RetrievalParamsC), u64, u32, u32, vp]
+    L.omr_encode_payloads.restype = i32; L.omr_encode_payloads.argtypes = [vp, vp, sz, vp, sz, u32, u32, vp]
+    L.omr_detect_batch_device.restype = i32; L.omr_detect_batch_device.argtypes = [vp, vp, vp, sz, vp, vp, P(StageTimes)]
+    L.omr_encode_indices_device.restype = i32
+    L.omr_encode_indices_device.argtypes = [vp, P(RetrievalParamsC), vp, sz, u64, u64, u32, u32, vp, vp]
+    L.omr_encode_payloads_device.restype = i32
+    L.omr_encode_payloads_device.argtypes = [vp, vp, vp, sz, u64, vp, sz, u32, u32, vp, vp]
+    L.omr_digest_reduce_mod.restype = i32; L.omr_digest_reduce_mod.argtypes = [vp, vp, sz, vp]
+    L.omr_l1_blind_rotate_device.restype = i32; L.omr_l1_blind_rotate_device.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.omr_keyswitch_device.restype = i32; L.omr_keyswitch_device.argtypes = [vp, vp, sz, vp, vp]
+    L.omr_l2_blind_rotate_device.restype = i32; L.omr_l2_blind_rotate_device.argtypes = [vp, vp, sz, vp, vp]
+    L.omr_trace_device.restype = i32; L.omr_trace_device.argtypes = [vp, vp, sz, vp]
+    L.omr_ntt_forward_device.restype = i32; L.omr_ntt_forward_device.argtypes = [vp, i32, vp, sz, vp]
+    L.omr_ntt_inverse_device.restype = i32; L.omr_ntt_inverse_device.argtypes = [vp, i32, vp, sz, vp]
+    _lib = L
+    return L

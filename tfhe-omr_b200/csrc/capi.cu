@@ -1,0 +1,495 @@
+// capi.cu — the C ABI of include/omr_b200.h over the kernels of kernels.cuh.  No CPU fallback anywhere: every
+// compute entry point launches CUDA kernels or returns OMR_ERR_CUDA.
+#include "../../include/omr_b200.h"
+#include "kernels.cuh"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+
+using namespace omr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- host-side constant tables (psi powers etc.) ------------------------------------------------------------------
+template <class T> struct HostWide;
+template <> struct HostWide<u32> { typedef u64 W; static constexpr int BITS = 32; };
+template <> struct HostWide<u64> { typedef u128 W; static constexpr int BITS = 64; };
+template <class T> T h_mulmod(T a, T b, T q) { return (T)((typename HostWide<T>::W)a * b % q); }
+template <class T> T h_powmod(T b, u64 e, T q) { T r = 1; while (e) { if (e & 1) r = h_mulmod(r, b, q); b = h_mulmod(b, b, q); e >>= 1; } return r; }
+template <class T> T h_shoup(T w, T q) { return (T)((((typename HostWide<T>::W)w) << HostWide<T>::BITS) / q); }
+unsigned h_bitrev(unsigned x, int bits) { unsigned r = 0; for (int i = 0; i < bits; ++i) { r = (r << 1) | (x & 1); x >>= 1; } return r; }
+
+// psi = g^((q-1)/2N) for the smallest g whose power has order exactly 2N; tables in bit-reversed order
+template <class T, class TW> void make_twiddles(int n, int logn, T q, std::vector<TW>& fwd, std::vector<TW>& inv) {
+    T psi = 0;
+    for (T g = 2;; ++g) { T c = h_powmod<T>(g, ((u64)q - 1) / (2 * (u64)n), q); if (h_powmod<T>(c, (u64)n, q) == q - 1) { psi = c; break; } }
+    T ipsi = h_powmod<T>(psi, (u64)q - 2, q);
+    std::vector<T> pw(n), ipw(n);
+    pw[0] = ipw[0] = 1;
+    for (int i = 1; i < n; ++i) { pw[i] = h_mulmod(pw[i - 1], psi, q); ipw[i] = h_mulmod(ipw[i - 1], ipsi, q); }
+    fwd.resize(n); inv.resize(n);
+    for (int i = 0; i < n; ++i) {
+        unsigned r = h_bitrev(i, logn);
+        fwd[i].x = pw[r]; fwd[i].y = h_shoup<T>(pw[r], q);
+        inv[i].x = ipw[r]; inv[i].y = h_shoup<T>(ipw[r], q);
+    }
+}
+
+#define CK(expr)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (expr);                                                                              \
+        if (e_ != cudaSuccess) { ctx_fail(ctx, std::string(#expr) + ": " + cudaGetErrorString(e_)); return OMR_ERR_CUDA; } \
+    } while (0)
+
+}  // namespace
+
+struct omr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    Tables tb{};
+    void *d_tw1 = nullptr, *d_itw1 = nullptr, *d_tw2 = nullptr, *d_itw2 = nullptr, *d_lut1 = nullptr, *d_lut2 = nullptr;
+    u32 *bsk1 = nullptr, *ksk = nullptr; u64 *bsk2 = nullptr, *trk = nullptr;   // internal (Montgomery * N^-1) forms
+    uint2 n1_inv{}; ulonglong2 n2_inv{};
+    size_t key_bytes = 0;
+    // scratch for the batched pipeline, sized for `cap` messages
+    size_t cap = 0; u32* s_rlwe1 = nullptr; u32* s_lwe2 = nullptr; unsigned short *s_ca = nullptr, *s_cb = nullptr;
+    // packing scratch
+    u64* s_partial = nullptr; size_t partial_words = 0;
+    u64* s_digest = nullptr; size_t digest_words = 0;
+    unsigned short *s_payloads = nullptr, *s_weights = nullptr; size_t payload_elems = 0, weight_elems = 0;
+    // resident pertinency store
+    u64* pv = nullptr; size_t pv_cap = 0, pv_count = 0; u64 pv_index0 = 0; bool pv_any = false;
+    cudaEvent_t ev[5] = {};
+    uint64_t launches = 0;
+};
+
+namespace {
+void ctx_fail(omr_ctx* ctx, const std::string& m) { if (ctx) ctx->err = m; else g_create_error = m; }
+
+template <class T> int dalloc(omr_ctx* ctx, T** p, size_t n) {
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    return OMR_OK;
+}
+
+int ensure_scratch(omr_ctx* ctx, size_t B) {
+    if (B <= ctx->cap) return OMR_OK;
+    cudaFree(ctx->s_rlwe1); cudaFree(ctx->s_lwe2); cudaFree(ctx->s_ca); cudaFree(ctx->s_cb);
+    ctx->cap = 0;
+    int st;
+    if ((st = dalloc(ctx, &ctx->s_rlwe1, B * 2 * F1::N))) return st;
+    if ((st = dalloc(ctx, &ctx->s_lwe2, B * LWE2_STRIDE_IN))) return st;
+    if ((st = dalloc(ctx, &ctx->s_ca, B * CLUE_N))) return st;
+    if ((st = dalloc(ctx, &ctx->s_cb, B * CLUE_COUNT))) return st;
+    ctx->cap = B;
+    return OMR_OK;
+}
+
+int ensure_pv(omr_ctx* ctx, size_t need) {
+    if (need <= ctx->pv_cap) return OMR_OK;
+    size_t ncap = ctx->pv_cap ? ctx->pv_cap : 1024;
+    while (ncap < need) ncap *= 2;
+    u64* np = nullptr;
+    CK(cudaMalloc((void**)&np, ncap * OMR_PV_WORDS * sizeof(u64)));
+    if (ctx->pv && ctx->pv_count)
+        CK(cudaMemcpyAsync(np, ctx->pv, ctx->pv_count * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->pv);
+    ctx->pv = np; ctx->pv_cap = ncap;
+    return OMR_OK;
+}
+
+// ---- launches -------------------------------------------------------------------------------------------------------
+int launch_l1(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* out, cudaStream_t s) {
+    if (!B) return OMR_OK;
+    l1_blind_rotate_kernel<<<(unsigned)B, L1_THREADS, L1_SMEM, s>>>(ca, cb, ctx->bsk1, out, ctx->tb);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s) {
+    if (!B) return OMR_OK;
+    dim3 grid((unsigned)((B + KS_MB - 1) / KS_MB), (KSK_PAD + KS_THREADS - 1) / KS_THREADS);
+    keyswitch_kernel<<<grid, KS_THREADS, 0, s>>>(rlwe, ctx->ksk, out, (int)B);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+int launch_l2(omr_ctx* ctx, const u32* lwe, size_t B, u64* out, cudaStream_t s) {
+    if (!B) return OMR_OK;
+    l2_blind_rotate_kernel<<<(unsigned)B, L2_THREADS, L2_SMEM, s>>>(lwe, ctx->bsk2, out, ctx->tb);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+int launch_trace(omr_ctx* ctx, u64* ct, size_t B, cudaStream_t s) {
+    if (!B) return OMR_OK;
+    trace_kernel<<<(unsigned)B, TR_THREADS, TR_SMEM, s>>>(ct, ctx->trk, ctx->tb);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
+int detect_device(omr_ctx* ctx, const unsigned short* d_ca, const unsigned short* d_cb, size_t B, u64* d_pv, cudaStream_t s,
+                  omr_stage_times* times) {
+    const size_t MAXB = 16384;                                  // per-launch batch (scratch bound)
+    int st;
+    if ((st = ensure_scratch(ctx, B < MAXB ? B : MAXB))) return st;
+    if (times) *times = omr_stage_times{};
+    for (size_t off = 0; off < B; off += MAXB) {
+        const size_t nb = B - off < MAXB ? B - off : MAXB;
+        if (times) CK(cudaEventRecord(ctx->ev[0], s));
+        if ((st = launch_l1(ctx, d_ca + off * CLUE_N, d_cb + off * CLUE_COUNT, nb, ctx->s_rlwe1, s))) return st;
+        if ((st = launch_ks(ctx, ctx->s_rlwe1, nb, ctx->s_lwe2, s))) return st;
+        if (times) CK(cudaEventRecord(ctx->ev[1], s));
+        if ((st = launch_l2(ctx, ctx->s_lwe2, nb, d_pv + off * OMR_PV_WORDS, s))) return st;
+        if (times) CK(cudaEventRecord(ctx->ev[2], s));
+        if ((st = launch_trace(ctx, d_pv + off * OMR_PV_WORDS, nb, s))) return st;
+        if (times) {
+            CK(cudaEventRecord(ctx->ev[3], s));
+            CK(cudaEventSynchronize(ctx->ev[3]));
+            float a = 0, b = 0, c = 0;
+            CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+            CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+            CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
+            times->first_level_bootstrapping_ms += a; times->second_level_bootstrapping_ms += b; times->trace_ms += c;
+            times->detect_ms += a + b + c;
+        }
+    }
+    return OMR_OK;
+}
+
+int ensure_partial(omr_ctx* ctx, size_t words) {
+    if (words <= ctx->partial_words) return OMR_OK;
+    cudaFree(ctx->s_partial); ctx->partial_words = 0;
+    int st; if ((st = dalloc(ctx, &ctx->s_partial, words))) return st;
+    ctx->partial_words = words;
+    return OMR_OK;
+}
+
+int pack_device(omr_ctx* ctx, bool indices, const u64* d_pv, size_t count, u64 index0, PackIndexArgs ia, PackPayloadArgs pa,
+                unsigned n_cipher, u64* d_out, cudaStream_t s) {
+    if (!n_cipher) return OMR_OK;
+    if (count == 0) { CK(cudaMemsetAsync(d_out, 0, (size_t)n_cipher * OMR_PV_WORDS * sizeof(u64), s)); return OMR_OK; }
+    const unsigned n_chunks = (unsigned)((count + PACK_CHUNK - 1) / PACK_CHUNK);
+    if (n_chunks > 65535u) { ctx_fail(ctx, "pack: too many messages for one call (max 65535*128)"); return OMR_ERR_INVALID; }
+    int st;
+    if ((st = ensure_partial(ctx, (size_t)n_cipher * n_chunks * OMR_PV_WORDS))) return st;
+    dim3 grid(n_cipher, n_chunks);
+    if (indices) pack_kernel<true><<<grid, PACK_THREADS, PACK_SMEM, s>>>(d_pv, count, index0, ia, pa, ctx->s_partial, ctx->tb);
+    else pack_kernel<false><<<grid, PACK_THREADS, PACK_SMEM, s>>>(d_pv, count, index0, ia, pa, ctx->s_partial, ctx->tb);
+    ++ctx->launches; CK(cudaGetLastError());
+    dim3 rgrid((OMR_PV_WORDS + 255) / 256, n_cipher);
+    reduce_partials_kernel<<<rgrid, 256, 0, s>>>(ctx->s_partial, (int)n_chunks, d_out);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
+int ensure_digest(omr_ctx* ctx, size_t words) {
+    if (words <= ctx->digest_words) return OMR_OK;
+    cudaFree(ctx->s_digest); ctx->digest_words = 0;
+    int st; if ((st = dalloc(ctx, &ctx->s_digest, words))) return st;
+    ctx->digest_words = words;
+    return OMR_OK;
+}
+
+int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_ctx** out) {
+    if (!keys || !out || !keys->bsk1 || !keys->ksk || !keys->bsk2 || !keys->trace) { g_create_error = "null argument"; return OMR_ERR_INVALID; }
+    if (keys->flags != OMR_KEYS_NTT_NATIVE && keys->flags != OMR_KEYS_COEFF) { g_create_error = "unknown key flags"; return OMR_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+        return OMR_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return OMR_ERR_INVALID; }
+    omr_ctx* ctx = new omr_ctx;
+    ctx->device = device;
+    auto fail = [&](int st) { g_create_error = ctx->err; omr_ctx_destroy(ctx); return st; };
+#define CKC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return fail(OMR_ERR_CUDA); } } while (0)
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& ev : ctx->ev) CKC(cudaEventCreate(&ev));
+    // constants
+    if ((u32)(Q1 * F1::QINV_NEG) != 0xFFFFFFFFu || (u64)(Q2 * F2::QINV_NEG) != ~0ull) { ctx->err = "bad Montgomery constants"; return fail(OMR_ERR_INVALID); }
+    std::vector<uint2> tw1, itw1; std::vector<ulonglong2> tw2, itw2;
+    make_twiddles<u32, uint2>(F1::N, F1::LOGN, Q1, tw1, itw1);
+    make_twiddles<u64, ulonglong2>(F2::N, F2::LOGN, Q2, tw2, itw2);
+    // LUTs: detector.rs:457-503 with lut.rs:12-27 (chunks of N>>log_t coefficients take v0,v1,v1,v2,v2,...)
+    std::vector<u32> lut1(F1::N, 0); std::vector<u64> lut2(F2::N, 0);
+    {
+        const u32 s1 = ((Q1 >> 4) + 1) >> 1, vals[5] = {s1, 0, 0, 0, Q1 - s1};
+        const int hd = F1::N >> 3;
+        for (int c = 0; c < F1::N / hd; ++c) { int vi = (c + 1) / 2; if (vi < 5) for (int j = 0; j < hd; ++j) lut1[c * hd + j] = vals[vi]; }
+        const u64 s2 = (2 * Q2 + OUT_P) / (2ull * OUT_P);        // round_half_up(q2 / 257), detector.rs:489-495
+        const int hd2 = F2::N >> 5;
+        for (int c = 0; c < F2::N / hd2; ++c) { int vi = (c + 1) / 2; if (vi == 2 * CLUE_COUNT) for (int j = 0; j < hd2; ++j) lut2[c * hd2 + j] = s2; }
+    }
+    auto upload = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t r = cudaMalloc(dst, bytes); if (r != cudaSuccess) return r;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    CKC(upload(&ctx->d_tw1, tw1.data(), tw1.size() * sizeof(uint2)));
+    CKC(upload(&ctx->d_itw1, itw1.data(), itw1.size() * sizeof(uint2)));
+    CKC(upload(&ctx->d_tw2, tw2.data(), tw2.size() * sizeof(ulonglong2)));
+    CKC(upload(&ctx->d_itw2, itw2.data(), itw2.size() * sizeof(ulonglong2)));
+    CKC(upload(&ctx->d_lut1, lut1.data(), lut1.size() * sizeof(u32)));
+    CKC(upload(&ctx->d_lut2, lut2.data(), lut2.size() * sizeof(u64)));
+    Tables& tb = ctx->tb;
+    tb.tw1 = (const uint2*)ctx->d_tw1; tb.itw1 = (const uint2*)ctx->d_itw1;
+    tb.tw2 = (const ulonglong2*)ctx->d_tw2; tb.itw2 = (const ulonglong2*)ctx->d_itw2;
+    tb.lut1 = (const u32*)ctx->d_lut1; tb.lut2 = (const u64*)ctx->d_lut2;
+    const u32 n1i = h_powmod<u32>(F1::N, Q1 - 2, Q1); const u64 n2i = h_powmod<u64>(F2::N, Q2 - 2, Q2);
+    ctx->n1_inv = make_uint2(n1i, h_shoup<u32>(n1i, Q1)); ctx->n2_inv = make_ulonglong2(n2i, h_shoup<u64>(n2i, Q2));
+    tb.n2_inv = ctx->n2_inv;
+    const u64 r2 = (u64)(((u128)1 << 64) % Q2); tb.r2 = make_ulonglong2(r2, h_shoup<u64>(r2, Q2));
+    for (int t = 0; t < TR_STEPS; ++t) {
+        const u32 d = (1u << (TR_STEPS - t)) + 1, M = 2 * F2::N; u32 inv = 1;
+        for (u32 x = 1; x < M; x += 2) if ((x * d) % M == 1) { inv = x; break; }
+        tb.trace_dinv[t] = inv;
+    }
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1_SMEM));
+    CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2_SMEM));
+    CKC(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM));
+    // keys -> internal form: every ring word * (R * N^-1) mod q; KSK padded to a 672-word row stride
+    const size_t n_bsk1 = (size_t)CLUE_N * 2 * G1::LEVELS * 2 * F1::N, n_ksk_rows = (size_t)F1::N * KS_LEVELS,
+                 n_bsk2 = (size_t)LWE2_N * 2 * G2::LEVELS * 2 * F2::N, n_trk = (size_t)TR_STEPS * TR_LEVELS * 2 * F2::N;
+    CKC(cudaMalloc((void**)&ctx->bsk1, n_bsk1 * 4)); CKC(cudaMalloc((void**)&ctx->ksk, n_ksk_rows * KSK_PAD * 4));
+    CKC(cudaMalloc((void**)&ctx->bsk2, n_bsk2 * 8)); CKC(cudaMalloc((void**)&ctx->trk, n_trk * 8));
+    ctx->key_bytes = n_bsk1 * 4 + n_ksk_rows * KSK_PAD * 4 + n_bsk2 * 8 + n_trk * 8;
+    const cudaMemcpyKind kind = keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaStream_t s = ctx->stream;
+    {
+        u32* tmp = nullptr; CKC(cudaMalloc((void**)&tmp, n_ksk_rows * LWE2_STRIDE_IN * 4));
+        CKC(cudaMemcpyAsync(tmp, keys->ksk, n_ksk_rows * LWE2_STRIDE_IN * 4, kind, s));
+        ksk_pad_kernel<<<(unsigned)((n_ksk_rows * KSK_PAD + 255) / 256), 256, 0, s>>>(tmp, ctx->ksk, n_ksk_rows); ++ctx->launches;
+        CKC(cudaStreamSynchronize(s)); cudaFree(tmp);
+    }
+    const bool coeff = keys->flags == OMR_KEYS_COEFF;
+    {
+        const u32 c1 = h_mulmod<u32>((u32)(((u64)1 << 32) % Q1), n1i, Q1);
+        CKC(cudaMemcpyAsync(ctx->bsk1, keys->bsk1, n_bsk1 * 4, kind, s));
+        if (coeff) { ntt_kernel<F1, false><<<(unsigned)(n_bsk1 / F1::N), F1::N / 8, F1::N * 4, s>>>(ctx->bsk1, tb, ctx->n1_inv); ++ctx->launches; }
+        scale_kernel<F1><<<(unsigned)((n_bsk1 + 255) / 256), 256, 0, s>>>(ctx->bsk1, ctx->bsk1, n_bsk1, make_uint2(c1, h_shoup<u32>(c1, Q1))); ++ctx->launches;
+        const u64 c2 = h_mulmod<u64>(r2, n2i, Q2); const ulonglong2 c2s = make_ulonglong2(c2, h_shoup<u64>(c2, Q2));
+        CKC(cudaMemcpyAsync(ctx->bsk2, keys->bsk2, n_bsk2 * 8, kind, s));
+        if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_bsk2 / F2::N), F2::N / 8, F2::N * 8, s>>>(ctx->bsk2, tb, ctx->n2_inv); ++ctx->launches; }
+        scale_kernel<F2><<<(unsigned)((n_bsk2 + 255) / 256), 256, 0, s>>>(ctx->bsk2, ctx->bsk2, n_bsk2, c2s); ++ctx->launches;
+        CKC(cudaMemcpyAsync(ctx->trk, keys->trace, n_trk * 8, kind, s));
+        if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_trk / F2::N), F2::N / 8, F2::N * 8, s>>>(ctx->trk, tb, ctx->n2_inv); ++ctx->launches; }
+        scale_kernel<F2><<<(unsigned)((n_trk + 255) / 256), 256, 0, s>>>(ctx->trk, ctx->trk, n_trk, c2s); ++ctx->launches;
+        CKC(cudaGetLastError());
+        CKC(cudaStreamSynchronize(s));
+    }
+#undef CKC
+    *out = ctx;
+    return OMR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int omr_ctx_create(int device, const omr_key_blobs* keys, omr_ctx** out) { return create_impl(device, keys, false, out); }
+int omr_ctx_create_device_keys(int device, const omr_key_blobs* keys, omr_ctx** out) { return create_impl(device, keys, true, out); }
+
+void omr_ctx_destroy(omr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
+                    ctx->s_rlwe1, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* omr_last_error(const omr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+size_t omr_detect_key_size(const omr_ctx* ctx) { return ctx ? ctx->key_bytes : 0; }
+uint64_t omr_launch_count(const omr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int omr_retrieval_params_init(uint64_t all_payloads_count, uint32_t pertinent_count, omr_retrieval_params* rp) {
+    if (!rp) return OMR_ERR_INVALID;
+    // RetrievalParams::new — parameters/retrieval_params.rs:50-106, with the constants of secret.rs:196-203
+    rp->index_modulus = OMR_P; rp->polynomial_size = OMR_N2; rp->bucket_count_per_segment = 130; rp->segment_count = 25;
+    rp->cmb_count_per_cipher = 2; rp->all_payloads_count = all_payloads_count; rp->pertinent_count = pertinent_count;
+    uint32_t e = 1; uint64_t pw = OMR_P;
+    while (pw < all_payloads_count) { pw *= OMR_P; ++e; }
+    rp->slots_per_bucket = e + 1;
+    rp->slots_per_segment = rp->slots_per_bucket * rp->bucket_count_per_segment;
+    rp->segment_per_cipher = rp->polynomial_size / rp->slots_per_segment;
+    rp->max_encode_indices_cipher_count = rp->segment_count / rp->segment_per_cipher;
+    rp->combination_count = pertinent_count + 5;
+    return OMR_OK;
+}
+
+// ---- device-pointer forms ----------------------------------------------------------------------------------------------
+int omr_detect_batch_device(omr_ctx* ctx, const uint16_t* d_clue_a, const uint16_t* d_clue_b, size_t B, uint64_t* d_pv, void* stream,
+                            omr_stage_times* times) {
+    if (!ctx || (B && (!d_clue_a || !d_clue_b || !d_pv))) { ctx_fail(ctx, "detect: null argument"); return OMR_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    return detect_device(ctx, d_clue_a, d_clue_b, B, (u64*)d_pv, (cudaStream_t)stream, times);
+}
+int omr_l1_blind_rotate_device(omr_ctx* ctx, const uint16_t* a, const uint16_t* b, size_t B, uint32_t* d_rlwe, void* stream) {
+    if (!ctx) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    return launch_l1(ctx, a, b, B, d_rlwe, (cudaStream_t)stream);
+}
+int omr_keyswitch_device(omr_ctx* ctx, const uint32_t* d_rlwe, size_t B, uint32_t* d_lwe, void* stream) {
+    if (!ctx) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    return launch_ks(ctx, d_rlwe, B, d_lwe, (cudaStream_t)stream);
+}
+int omr_l2_blind_rotate_device(omr_ctx* ctx, const uint32_t* d_lwe, size_t B, uint64_t* d_rlwe, void* stream) {
+    if (!ctx) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    return launch_l2(ctx, d_lwe, B, (u64*)d_rlwe, (cudaStream_t)stream);
+}
+int omr_trace_device(omr_ctx* ctx, uint64_t* d_rlwe, size_t B, void* stream) {
+    if (!ctx) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    return launch_trace(ctx, (u64*)d_rlwe, B, (cudaStream_t)stream);
+}
+int omr_ntt_forward_device(omr_ctx* ctx, int level, void* d, size_t batch, void* stream) {
+    if (!ctx || (level != 1 && level != 2)) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!batch) return OMR_OK;
+    if (level == 1) ntt_kernel<F1, false><<<(unsigned)batch, F1::N / 8, F1::N * 4, s>>>((u32*)d, ctx->tb, ctx->n1_inv);
+    else ntt_kernel<F2, false><<<(unsigned)batch, F2::N / 8, F2::N * 8, s>>>((u64*)d, ctx->tb, ctx->n2_inv);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d, size_t batch, void* stream) {
+    if (!ctx || (level != 1 && level != 2)) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!batch) return OMR_OK;
+    if (level == 1) ntt_kernel<F1, true><<<(unsigned)batch, F1::N / 8, F1::N * 4, s>>>((u32*)d, ctx->tb, ctx->n1_inv);
+    else ntt_kernel<F2, true><<<(unsigned)batch, F2::N / 8, F2::N * 8, s>>>((u64*)d, ctx->tb, ctx->n2_inv);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
+static int check_rp(omr_ctx* ctx, const omr_retrieval_params* rp) {
+    // encode_pertinent_indices asserts polynomial_size == ntt dimension (detector.rs:236)
+    if (!rp || rp->polynomial_size != (uint32_t)OMR_N2 || rp->index_modulus != OMR_P || rp->slots_per_bucket < 2 ||
+        rp->slots_per_segment != rp->slots_per_bucket * rp->bucket_count_per_segment ||
+        rp->segment_per_cipher * rp->slots_per_segment > (uint32_t)OMR_N2 || rp->segment_per_cipher == 0) {
+        ctx_fail(ctx, "invalid retrieval params"); return OMR_ERR_INVALID;
+    }
+    return OMR_OK;
+}
+
+int omr_encode_indices_device(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* d_pv, size_t count, uint64_t index0,
+                              uint64_t seed, uint32_t cipher_idx0, uint32_t n_cipher, uint64_t* d_out, void* stream) {
+    if (!ctx || !d_out || (count && !d_pv)) { ctx_fail(ctx, "encode_indices: null argument"); return OMR_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    int st; if ((st = check_rp(ctx, rp))) return st;
+    PackIndexArgs ia{rp->slots_per_bucket, rp->slots_per_segment, rp->segment_per_cipher, rp->bucket_count_per_segment, seed, cipher_idx0};
+    return pack_device(ctx, true, (const u64*)d_pv, count, index0, ia, PackPayloadArgs{}, n_cipher, (u64*)d_out,
+                       (cudaStream_t)stream);
+}
+int omr_encode_payloads_device(omr_ctx* ctx, const uint64_t* d_pv, const uint16_t* d_payloads, size_t count, uint64_t index0,
+                               const uint16_t* d_weights, size_t weight_stride, uint32_t n_cipher, uint32_t cmb_per_cipher, uint64_t* d_out,
+                               void* stream) {
+    if (!ctx || !d_out || (count && (!d_pv || !d_payloads || !d_weights))) { ctx_fail(ctx, "encode_payloads: null argument"); return OMR_ERR_INVALID; }
+    if (cmb_per_cipher == 0 || cmb_per_cipher * OMR_PAYLOAD_LEN > OMR_N2 || index0 + count > weight_stride) {
+        ctx_fail(ctx, "encode_payloads: bad combination layout"); return OMR_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    PackPayloadArgs pa{d_payloads, d_weights, weight_stride, cmb_per_cipher};
+    return pack_device(ctx, false, (const u64*)d_pv, count, index0, PackIndexArgs{}, pa, n_cipher, (u64*)d_out,
+                       (cudaStream_t)stream);
+}
+int omr_digest_reduce_mod(omr_ctx* ctx, uint64_t* d_words, size_t n, void* stream) {
+    if (!ctx || (n && !d_words)) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    if (!n) return OMR_OK;
+    digest_mod_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((u64*)d_words, n);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
+// ---- host-buffer forms ---------------------------------------------------------------------------------------------------
+int omr_pv_reset(omr_ctx* ctx) {
+    if (!ctx) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->pv_count = 0; ctx->pv_any = false; ctx->pv_index0 = 0;
+    return OMR_OK;
+}
+
+int omr_detect_batch(omr_ctx* ctx, const uint16_t* clue_a, const uint16_t* clue_b, size_t B, uint64_t global_index0, uint64_t* pv_out,
+                     omr_stage_times* times) {
+    if (!ctx || (B && (!clue_a || !clue_b))) { ctx_fail(ctx, "detect: null argument"); return OMR_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (times) *times = omr_stage_times{};
+    if (!B) return OMR_OK;
+    // the store holds one contiguous run of global indices
+    if (!ctx->pv_any) { ctx->pv_index0 = global_index0; ctx->pv_count = 0; }
+    if (global_index0 != ctx->pv_index0 + ctx->pv_count) { ctx_fail(ctx, "detect: global_index0 must continue the pertinency store"); return OMR_ERR_STATE; }
+    int st;
+    if ((st = ensure_pv(ctx, ctx->pv_count + B))) return st;
+    const size_t MAXB = 16384;
+    if ((st = ensure_scratch(ctx, B < MAXB ? B : MAXB))) return st;
+    cudaStream_t s = ctx->stream;
+    for (size_t off = 0; off < B; off += MAXB) {
+        const size_t nb = B - off < MAXB ? B - off : MAXB;
+        CK(cudaMemcpyAsync(ctx->s_ca, clue_a + off * CLUE_N, nb * CLUE_N * 2, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->s_cb, clue_b + off * CLUE_COUNT, nb * CLUE_COUNT * 2, cudaMemcpyHostToDevice, s));
+        u64* dst = ctx->pv + (ctx->pv_count + off) * OMR_PV_WORDS;
+        omr_stage_times tt;
+        if ((st = detect_device(ctx, ctx->s_ca, ctx->s_cb, nb, dst, s, times ? &tt : nullptr))) return st;
+        if (times) {
+            times->detect_ms += tt.detect_ms; times->first_level_bootstrapping_ms += tt.first_level_bootstrapping_ms;
+            times->second_level_bootstrapping_ms += tt.second_level_bootstrapping_ms; times->trace_ms += tt.trace_ms;
+        }
+        if (pv_out) CK(cudaMemcpyAsync(pv_out + off * OMR_PV_WORDS, dst, nb * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));       // scratch clue buffers are reused by the next chunk
+    }
+    ctx->pv_count += B; ctx->pv_any = true;
+    return OMR_OK;
+}
+
+int omr_encode_indices(omr_ctx* ctx, const omr_retrieval_params* rp, uint64_t seed, uint32_t cipher_idx0, uint32_t n_cipher, uint64_t* out) {
+    if (!ctx || !out) { ctx_fail(ctx, "encode_indices: null argument"); return OMR_ERR_INVALID; }
+    int st;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+        if (!ctx->pv_any) { ctx_fail(ctx, "encode_indices: empty pertinency store"); return OMR_ERR_STATE; }
+        if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
+    }
+    if ((st = omr_encode_indices_device(ctx, rp, ctx->pv, ctx->pv_count, ctx->pv_index0, seed, cipher_idx0, n_cipher, ctx->s_digest, ctx->stream))) return st;
+    CK(cudaMemcpyAsync(out, ctx->s_digest, (size_t)n_cipher * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return OMR_OK;
+}
+
+int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, const uint16_t* weights, size_t weight_stride, uint32_t n_cipher,
+                        uint32_t cmb_per_cipher, uint64_t* out) {
+    if (!ctx || !out || !payloads || !weights) { ctx_fail(ctx, "encode_payloads: null argument"); return OMR_ERR_INVALID; }
+    int st;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+        if (!ctx->pv_any) { ctx_fail(ctx, "encode_payloads: empty pertinency store"); return OMR_ERR_STATE; }
+        if (count != ctx->pv_count) { ctx_fail(ctx, "encode_payloads: payload count != pertinency store size"); return OMR_ERR_INVALID; }
+        if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
+        const size_t pe = count * OMR_PAYLOAD_LEN, we = (size_t)n_cipher * cmb_per_cipher * weight_stride;
+        if (pe > ctx->payload_elems) { cudaFree(ctx->s_payloads); ctx->payload_elems = 0; if ((st = dalloc(ctx, &ctx->s_payloads, pe))) return st; ctx->payload_elems = pe; }
+        if (we > ctx->weight_elems) { cudaFree(ctx->s_weights); ctx->weight_elems = 0; if ((st = dalloc(ctx, &ctx->s_weights, we))) return st; ctx->weight_elems = we; }
+        CK(cudaMemcpyAsync(ctx->s_payloads, payloads, pe * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->s_weights, weights, we * 2, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((st = omr_encode_payloads_device(ctx, ctx->pv, ctx->s_payloads, count, ctx->pv_index0, ctx->s_weights, weight_stride, n_cipher, cmb_per_cipher,
+                                         ctx->s_digest, ctx->stream))) return st;
+    CK(cudaMemcpyAsync(out, ctx->s_digest, (size_t)n_cipher * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return OMR_OK;
+}
+
+}  // extern "C"
