@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — detected messages/sec of the InstantOMR detection hot path at D = 65 536 (BASELINE.json configs[3]).
+
+    python bench.py --gpus N --steps K --warmup W             (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (the CPU arm: the oracle port on all host cores)
+
+One step = one pass of the hot path (detect -> index digest -> payload digest [-> NCCL sum of partial digests])
+over one launch batch of M = 8 192 messages of the 65 536-message board, per GPU (weak scaling: every rank works on
+its own slice of the board; the only collective is the sum of the 33 partial digest ciphertexts).
+`value` times the step with inputs resident in HBM; `e2e` times the same step through the host-buffer C ABI
+(omr_detect_batch / omr_encode_indices / omr_encode_payloads) with pinned host inputs and the digest read back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_BOARD = 65536
+PERTINENT = 50
+Q1, Q2 = 134215681, 1125899906826241
+METRIC = "detected messages/sec at D=65536"
+README_SINGLE_CORE_MSGS = 65536 / 15340.2083335          # /root/reference README.md:120-121 -> 4.272 msg/s
+
+# algorithmic work per message
+M32 = 242_221_056          # 32-bit mulmods (L1 blind rotations)
+M64 = 143_082_496          # 64-bit mulmods (L2 blind rotation + trace + final NTTs)
+BSK2_BYTES = 670 * 12 * 2 * 2048 * 8
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _pinned(shape, dtype):
+    import torch
+    return torch.empty(shape, dtype=dtype).pin_memory()
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import tfhe_omr_b200 as omr
+    from tfhe_omr_b200.detector import BSK1_SHAPE, KSK_SHAPE, BSK2_SHAPE, TRACE_SHAPE
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: tfhe_omr_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    M = args.messages_per_step
+    n_slices = D_BOARD // M
+
+    # synthetic inputs: uniformly random keys / clues (the path is data-oblivious integer arithmetic);
+    # the same keys on every rank (they are replicated per GPU in a deployment)
+    g = torch.Generator(device=dev); g.manual_seed(20261018)
+    bsk1 = torch.randint(0, Q1, BSK1_SHAPE, dtype=torch.int32, device=dev, generator=g)
+    ksk = torch.randint(0, Q1, KSK_SHAPE, dtype=torch.int32, device=dev, generator=g)
+    bsk2 = torch.randint(0, Q2, BSK2_SHAPE, dtype=torch.int64, device=dev, generator=g)
+    trk = torch.randint(0, Q2, TRACE_SHAPE, dtype=torch.int64, device=dev, generator=g)
+    det = omr.Detector(omr.DetectionKey(bsk1, ksk, bsk2, trk), device=local)
+    key_host = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        key_host = [t.cpu().numpy() for t in (bsk1, ksk, bsk2, trk)]
+    del bsk1, ksk, bsk2, trk
+    g.manual_seed(1000 + rank)
+    clue_a = torch.randint(0, 2048, (M, 512), dtype=torch.int16, device=dev, generator=g)
+    clue_b = torch.randint(0, 2048, (M, 7), dtype=torch.int16, device=dev, generator=g)
+    payloads = torch.randint(0, 256, (M, 612), dtype=torch.int16, device=dev, generator=g)
+    g.manual_seed(77)
+    rp = omr.RetrievalParams(D_BOARD, PERTINENT)
+    n_idx, n_pay = rp.max_encode_indices_cipher_count, rp.payload_cipher_count
+    weights = torch.zeros((n_pay * rp.cmb_count_per_cipher, D_BOARD), dtype=torch.int16, device=dev)
+    weights[:rp.combination_count] = torch.randint(0, 257, (rp.combination_count, D_BOARD), dtype=torch.int16, device=dev, generator=g)
+    digest = torch.zeros((n_idx + n_pay, 2, 2048), dtype=torch.int64, device=dev)
+    # pinned host copies for the e2e arm
+    h_a, h_b, h_p, h_w = (_pinned(t.shape, t.dtype) for t in (clue_a, clue_b, payloads, weights))
+    for h, d in ((h_a, clue_a), (h_b, clue_b), (h_p, payloads), (h_w, weights)):
+        h.copy_(d)
+    h_digest = _pinned(digest.shape, digest.dtype)
+    torch.cuda.synchronize()
+
+    times = omr.DetectTimeInfo()
+
+    def step_resident(i, t=None):
+        sl = (i * world + rank) % n_slices
+        pv = det.detect((clue_a, clue_b), index0=sl * M, times=t)
+        det.encode_pertinent_indices(rp, pv, seed=0xC0FFEE, cipher_index=0, n_cipher=n_idx, out=digest[:n_idx])
+        det.encode_pertinent_payloads(pv, payloads, rp.combination_count, rp.cmb_count_per_cipher, weights, out=digest[n_idx:])
+        if world > 1:
+            dist.all_reduce(digest)                      # NCCL sum of the partial digests (values < q2 < 2^50)
+            det.digest_reduce_mod(digest)
+        return pv
+
+    def step_e2e(i):
+        sl = (i * world + rank) % n_slices
+        det.pv_reset()
+        det.detect_host(h_a.numpy(), h_b.numpy(), global_index0=sl * M)
+        di = det.encode_indices_host(rp, 0xC0FFEE, 0, n_idx)
+        dp = det.encode_payloads_host(h_p.numpy(), h_w.numpy(), rp.combination_count, rp.cmb_count_per_cipher)
+        if world > 1:
+            digest[:n_idx].copy_(torch.from_numpy(di.view(np.int64))); digest[n_idx:].copy_(torch.from_numpy(dp.view(np.int64)))
+            dist.all_reduce(digest); det.digest_reduce_mod(digest)
+            h_digest.copy_(digest); torch.cuda.synchronize()
+        return di, dp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    # ---- resident arm --------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = det.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_resident(args.warmup + i, times)
+    ev1.record()
+    barrier()
+    launches = det.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = ms_total / args.steps
+    value = world * M * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e arm (host buffers through the C ABI) -------------------------------------------------------------------
+    for i in range(min(args.warmup, 1)):
+        step_e2e(i)
+    barrier()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = world * M * e2e_steps / (e2e_ms * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in (h_a, h_b, h_p)) + n_pay * rp.cmb_count_per_cipher * D_BOARD * 2
+    d2h = digest.numel() * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines for the dominant kernel (L2 blind rotation; ~2/3 of the step) -------------------------------------
+    peaks, peak_src = _peaks()
+    l2_ms = times.total_second_level_bootstrapping_time / args.steps          # CUDA events on the launching stream
+    l1_ms = times.total_first_level_bootstrapping_time / args.steps
+    alg_bytes = BSK2_BYTES + M * (671 * 4 + 2 * 2048 * 8)                     # key pass once per launch + LWE in + RLWE out
+    hbm_achieved = alg_bytes / (l2_ms * 1e-3) / 1e9
+    p32 = det.mulmod_peak(1); p64 = det.mulmod_peak(2)
+    t_roof = M32 / p32 + M64 / p64                                            # seconds per message at the measured integer peak
+    t_meas = ms_per_step * 1e-3 / M
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "messages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": round(value / README_SINGLE_CORE_MSGS, 2), "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "omr --payload-count 65536 (BASELINE.json configs[3]): detect + index/payload digest", "D": D_BOARD,
+                   "messages_per_step_per_gpu": M, "pertinent": PERTINENT, "index_ciphertexts": n_idx, "payload_ciphertexts": n_pay,
+                   "parallelism": f"message-sharded x{world}, keys replicated, NCCL sum of partial digests",
+                   "l2": "per-step working set (keys 363 MiB + pertinency vector %d MiB) exceeds the 126 MB L2; no flush" % (M * 32768 // 2**20),
+                   "vs_baseline_ref": "reference README.md:120-121, single-core detect 4.272 msg/s (unnamed AVX-512 CPU)"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "messages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "l2_blind_rotate_kernel", "achieved": round(hbm_achieved, 3), "peak": peaks.get("hbm_gbs"),
+                     "unit": "GB/s", "frac": round(hbm_achieved / peaks.get("hbm_gbs"), 6), "traffic": None, "peak_source": peak_src,
+                     "kernel_ms_per_launch": round(l2_ms, 3), "kernel_share_of_step": round(l2_ms / ms_per_step, 3),
+                     "note": "integer-issue bound, not HBM bound: see roofline_int"},
+        "roofline_int": {"bound": "int-pipe", "achieved": round(1.0 / t_meas, 1), "peak": round(1.0 / t_roof, 1), "unit": "messages/s/GPU",
+                         "frac": round(t_roof / t_meas, 4), "peak_mulmod32_per_s": p32, "peak_mulmod64_per_s": p64,
+                         "per_message": {"mulmod32": M32, "mulmod64": M64},
+                         "stage_ms_per_step": {"first_level": round(l1_ms, 2), "second_level": round(l2_ms, 2),
+                                               "trace": round(times.total_trace_time / args.steps, 2)}},
+    }
+    if key_host is not None:
+        line["cpu_baseline"] = cpu_baseline(key_host, args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(key_host, args, steps=1, native=True):
+    """Oracle (CPU port of the reference's detect) on a bounded sample, all host cores, one message per thread as
+    rayon does in examples/omr.rs:67-70,160-164."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle as O
+    try:
+        O.build(native=native)
+    except Exception:
+        native = False
+    cores = os.cpu_count() or 1
+    sample = max(2, min(args.cpu_sample, 2 * cores))
+    kp = O.KeyPack(blobs=key_host, native=native)
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 2048, (sample, 512), dtype=np.uint16); b = rng.integers(0, 2048, (sample, 7), dtype=np.uint16)
+    t0 = time.perf_counter(); kp.detect(a[:1], b[:1], threads=1); t1 = time.perf_counter() - t0
+    best = None
+    for _ in range(steps):
+        t0 = time.perf_counter(); kp.detect(a, b, threads=cores); dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": round(sample / best, 3), "unit": "messages/s", "cores": cores, "kind": "port",
+            "sample": f"oracle detect (C++ port of detector.rs:135-166, {'-march=native' if native else 'portable'} build) on {sample} messages, "
+                      f"{cores} threads; single-thread latency {t1 * 1e3:.0f} ms/message; packing not included (0.2% of the reference's time)",
+            "single_thread_ms_per_message": round(t1 * 1e3, 1)}
+
+
+def run_reference(args):
+    """The reference arm: the reference's own CPU implementation cannot be built here (Rust + un-vendored Primus-fhe),
+    so this times the oracle port on all host cores, same metric/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle as O
+    native = True
+    try:
+        O.build(native=True)
+    except Exception:
+        native = False
+    cores = os.cpu_count() or 1
+    sample = max(2, min(args.cpu_sample, 2 * cores))
+    kp = O.KeyPack(blobs=O.random_key_blobs(20261018), native=native)
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 2048, (sample, 512), dtype=np.uint16); b = rng.integers(0, 2048, (sample, 7), dtype=np.uint16)
+    for _ in range(min(args.warmup, 1)):
+        kp.detect(a[:cores], b[:cores], threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        kp.detect(a, b, threads=cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = (f"oracle detect (C++ port, {'-march=native' if native else 'portable'}) on {sample} messages per step, {cores} threads "
+            f"(one message per thread, examples/omr.rs:160-164)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "messages/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": round(value / README_SINGLE_CORE_MSGS, 3), "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "omr --payload-count 65536 (BASELINE.json configs[3]): detect", "D": D_BOARD, "messages_per_step": sample},
+        "cpu_baseline": {"value": round(value, 3), "unit": "messages/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": round(value, 3), "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--messages-per-step", type=int, default=8192)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if D_BOARD % args.messages_per_step:
+        raise SystemExit("--messages-per-step must divide 65536")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,10 @@ int omr_trace_device(omr_ctx* ctx, uint64_t* d_rlwe /*[B][2][2048], in place -> 
 int omr_ntt_forward_device(omr_ctx* ctx, int level, void* d_data, size_t batch, void* stream);
 int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d_data, size_t batch, void* stream);
 
+/* Step-0 peak: sustained rate of the register-only Shoup butterfly loop the NTTs are made of,
+ * level 1 = 32-bit (q1), level 2 = 64-bit (q2); the denominator of the integer-pipe roofline in bench.py. */
+int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_second);
+
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
 uint64_t omr_launch_count(const omr_ctx* ctx);
 

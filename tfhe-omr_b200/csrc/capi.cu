@@ -492,4 +492,23 @@ int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, co
     return OMR_OK;
 }
 
+int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_second) {
+    if (!ctx || !mulmods_per_second || (level != 1 && level != 2) || iters <= 0) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    int st; if ((st = ensure_digest(ctx, (size_t)blocks * threads))) return st;
+    cudaStream_t s = ctx->stream;
+    for (int rep = 0; rep < 2; ++rep) {          // first run warms up
+        CK(cudaEventRecord(ctx->ev[0], s));
+        if (level == 1) mulmod_peak_kernel<F1><<<blocks, threads, 0, s>>>((u32*)ctx->s_digest, ctx->n1_inv, iters);
+        else mulmod_peak_kernel<F2><<<blocks, threads, 0, s>>>((u64*)ctx->s_digest, ctx->n2_inv, iters);
+        ++ctx->launches; CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[1], s)); CK(cudaEventSynchronize(ctx->ev[1]));
+    }
+    float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    *mulmods_per_second = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+    return OMR_OK;
+}
+
 }  // extern "C"

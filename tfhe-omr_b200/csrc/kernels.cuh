@@ -488,4 +488,32 @@ __global__ void ksk_pad_kernel(const u32* __restrict__ in, u32* __restrict__ out
     out[i] = c < (size_t)LWE2_STRIDE_IN ? in[r * LWE2_STRIDE_IN + c] : 0u;
 }
 
+// ---- step-0 peak: register-only loop of the Shoup butterfly the NTTs use (the denominator of the integer roofline) --
+// every thread runs 8 independent forward butterflies per iteration (= 8 mulmods + their add/sub), no memory traffic.
+template <class F>
+__global__ void __launch_bounds__(256) mulmod_peak_kernel(typename F::T* sink, typename F::TW w0, int iters) {
+    typedef typename F::T T;
+    T x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (T)(threadIdx.x * 8 + k + 1);
+    typename F::TW w = w0;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            T u = x[k], v = F::mul_shoup(x[k + 4], w);
+            x[k] = u + v; x[k + 4] = u - v + 2 * F::Q;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            T u = x[k], v = F::mul_shoup(x[k + 1], w);
+            x[k] = F::canon_lazy(u + v); x[k + 1] = F::canon_lazy(u - v + 2 * F::Q);
+        }
+    }
+    T acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += x[k];
+    if (acc == (T)0x12345) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 }  // namespace omr

@@ -263,6 +263,12 @@ class Detector:
         self._ck(self.L.omr_trace_device(self.h, rlwe.data_ptr(), rlwe.shape[0], self._stream()))
         return rlwe
 
+    def mulmod_peak(self, level, iters=20000):
+        """Measured peak of the register-only Shoup butterfly loop (mulmods/s) — the integer roofline denominator."""
+        v = C.c_double(0.0)
+        self._ck(self.L.omr_mulmod_peak(self.h, level, iters, C.byref(v)))
+        return v.value
+
     def ntt(self, level, data, inverse=False):
         fn = self.L.omr_ntt_inverse_device if inverse else self.L.omr_ntt_forward_device
         self._ck(fn(self.h, level, data.data_ptr(), data.shape[0], self._stream()))
