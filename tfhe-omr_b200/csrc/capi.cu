@@ -53,8 +53,8 @@ struct omr_ctx {
     std::mutex mu;
     std::string err;
     Tables tb{};
-    void *d_tw1 = nullptr, *d_itw1 = nullptr, *d_tw2 = nullptr, *d_itw2 = nullptr, *d_lut1 = nullptr, *d_lut2 = nullptr;
-    u32 *bsk1 = nullptr, *ksk = nullptr; u64 *bsk2 = nullptr, *trk = nullptr;   // internal (Montgomery * N^-1) forms
+    void *d_tw1 = nullptr, *d_itw1 = nullptr, *d_tw2 = nullptr, *d_itw2 = nullptr, *d_lut1 = nullptr, *d_lut2 = nullptr, *d_tw2d = nullptr, *d_itw2d = nullptr;
+    u32 *bsk1 = nullptr, *ksk = nullptr; u64 *bsk2 = nullptr, *trk = nullptr;   // internal forms: bsk1/trk Montgomery * N^-1; bsk2 = centred doubles * N^-1
     uint2 n1_inv{}; ulonglong2 n2_inv{};
     size_t key_bytes = 0;
     // scratch for the batched pipeline, sized for `cap` messages
@@ -120,7 +120,7 @@ int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s)
 }
 int launch_l2(omr_ctx* ctx, const u32* lwe, size_t B, u64* out, cudaStream_t s) {
     if (!B) return OMR_OK;
-    l2_blind_rotate_kernel<<<(unsigned)B, L2_THREADS, L2_SMEM, s>>>(lwe, ctx->bsk2, out, ctx->tb);
+    l2_blind_rotate_kernel<<<(unsigned)B, L2_THREADS, L2_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out, ctx->tb);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
@@ -235,11 +235,22 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     CKC(upload(&ctx->d_itw1, itw1.data(), itw1.size() * sizeof(uint2)));
     CKC(upload(&ctx->d_tw2, tw2.data(), tw2.size() * sizeof(ulonglong2)));
     CKC(upload(&ctx->d_itw2, itw2.data(), itw2.size() * sizeof(ulonglong2)));
+    {   // FP64-path twiddles: centred w and w/q2 (division in long double, rounded once to double)
+        std::vector<double2> t2d(F2::N), it2d(F2::N);
+        auto cen = [](u64 v) { return v > (Q2 >> 1) ? -(double)(int64_t)(Q2 - v) : (double)(int64_t)v; };
+        for (int i = 0; i < F2::N; ++i) {
+            t2d[i].x = cen(tw2[i].x); t2d[i].y = (double)((long double)t2d[i].x / (long double)Q2);
+            it2d[i].x = cen(itw2[i].x); it2d[i].y = (double)((long double)it2d[i].x / (long double)Q2);
+        }
+        CKC(upload(&ctx->d_tw2d, t2d.data(), t2d.size() * sizeof(double2)));
+        CKC(upload(&ctx->d_itw2d, it2d.data(), it2d.size() * sizeof(double2)));
+    }
     CKC(upload(&ctx->d_lut1, lut1.data(), lut1.size() * sizeof(u32)));
     CKC(upload(&ctx->d_lut2, lut2.data(), lut2.size() * sizeof(u64)));
     Tables& tb = ctx->tb;
     tb.tw1 = (const uint2*)ctx->d_tw1; tb.itw1 = (const uint2*)ctx->d_itw1;
     tb.tw2 = (const ulonglong2*)ctx->d_tw2; tb.itw2 = (const ulonglong2*)ctx->d_itw2;
+    tb.tw2d = (const double2*)ctx->d_tw2d; tb.itw2d = (const double2*)ctx->d_itw2d;
     tb.lut1 = (const u32*)ctx->d_lut1; tb.lut2 = (const u64*)ctx->d_lut2;
     const u32 n1i = h_powmod<u32>(F1::N, Q1 - 2, Q1); const u64 n2i = h_powmod<u64>(F2::N, Q2 - 2, Q2);
     ctx->n1_inv = make_uint2(n1i, h_shoup<u32>(n1i, Q1)); ctx->n2_inv = make_ulonglong2(n2i, h_shoup<u64>(n2i, Q2));
@@ -276,7 +287,7 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         const u64 c2 = h_mulmod<u64>(r2, n2i, Q2); const ulonglong2 c2s = make_ulonglong2(c2, h_shoup<u64>(c2, Q2));
         CKC(cudaMemcpyAsync(ctx->bsk2, keys->bsk2, n_bsk2 * 8, kind, s));
         if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_bsk2 / F2::N), F2::N / 8, F2::N * 8, s>>>(ctx->bsk2, tb, ctx->n2_inv); ++ctx->launches; }
-        scale_kernel<F2><<<(unsigned)((n_bsk2 + 255) / 256), 256, 0, s>>>(ctx->bsk2, ctx->bsk2, n_bsk2, c2s); ++ctx->launches;
+        key_to_double_kernel<<<(unsigned)((n_bsk2 + 255) / 256), 256, 0, s>>>(ctx->bsk2, reinterpret_cast<double*>(ctx->bsk2), n_bsk2, ctx->n2_inv); ++ctx->launches;
         CKC(cudaMemcpyAsync(ctx->trk, keys->trace, n_trk * 8, kind, s));
         if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_trk / F2::N), F2::N / 8, F2::N * 8, s>>>(ctx->trk, tb, ctx->n2_inv); ++ctx->launches; }
         scale_kernel<F2><<<(unsigned)((n_trk + 255) / 256), 256, 0, s>>>(ctx->trk, ctx->trk, n_trk, c2s); ++ctx->launches;
@@ -299,7 +310,7 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
+    void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
                     ctx->s_rlwe1, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);

@@ -87,4 +87,44 @@ struct F2 {
     static __device__ __forceinline__ T add_canon(T a, T d) { T v = a + fold(d); v = csub(v, Q); return csub(v, Q); }
 };
 
+// ---- level 2 on the FP64 pipe ---------------------------------------------------------------------------------------
+// B200 issues 64 DFMA/clk/SM (measured, profiles/r1_pipe_microbench.txt) while a 64-bit integer mulmod costs ~48 issue
+// slots (mul.hi.u64 runs at 7.6/clk/SM).  Residues mod q2 < 2^50 are therefore carried as integer-valued doubles and
+// multiplied with error-free transformations (two-product by FMA + quotient by the 1.5*2^52 rounding constant): every
+// result is an exact integer, so the arithmetic is still exact mod q2 and bit-identical to the integer oracle.
+// Invariants: every value is an integer with |x| < 2^53; inputs of mulmod have |x| < 2^52 (= 4q).
+struct D2 {
+    static constexpr double Q = 1125899906826241.0;
+    static constexpr double QINV = 1.0 / 1125899906826241.0;
+    static constexpr double MAGIC = 6755399441055744.0;        // 1.5 * 2^52: (v + MAGIC) - MAGIC = rint(v) for |v| <= 2^51
+    // x * w mod q for a constant w (|w| <= q/2) with winv = w/q; |x| < 4q  ->  |result| < 0.76 q
+    static __device__ __forceinline__ double mulmod(double x, double w, double winv) {
+        const double h = __dmul_rn(x, w);
+        const double l = __fma_rn(x, w, -h);                                   // x*w = h + l exactly
+        const double k = __dadd_rn(__fma_rn(x, winv, MAGIC), -MAGIC);          // rint(x*w/q) +- 0.25
+        return __dadd_rn(__fma_rn(-k, Q, h), l);                               // exact: both terms are small integers
+    }
+    // x * key mod q for a key word without a precomputed quotient (|x| <= 1.3q, |key| <= q/2) -> |result| < 0.66 q
+    static __device__ __forceinline__ double mulmod_key(double x, double key) {
+        const double h = __dmul_rn(x, key);
+        const double l = __fma_rn(x, key, -h);
+        const double k = __dadd_rn(__fma_rn(h, QINV, MAGIC), -MAGIC);
+        return __dadd_rn(__fma_rn(-k, Q, h), l);
+    }
+    // x -> x - rint(x/q) q : |x| < 8q -> |result| <= q/2 (+1)
+    static __device__ __forceinline__ double renorm(double x) {
+        const double k = __dadd_rn(__fma_rn(x, QINV, MAGIC), -MAGIC);
+        return __fma_rn(-k, Q, x);
+    }
+    // small signed integer (|d| < 2^31) -> double without a cvt instruction
+    static __device__ __forceinline__ double from_small(int d) {
+        return __dadd_rn(__hiloint2double(0x43300000, d + (1 << 20)), -(4503599627370496.0 + 1048576.0));
+    }
+    // integer-valued double, |x| < 2^51 -> int64 without a cvt instruction
+    static __device__ __forceinline__ i64 to_i64(double x) {
+        const u64 b = (u64)__double_as_longlong(__dadd_rn(x, MAGIC));          // mantissa = 2^51 + x
+        return (i64)(b & ((1ull << 52) - 1)) - ((i64)1 << 51);
+    }
+};
+
 }  // namespace omr

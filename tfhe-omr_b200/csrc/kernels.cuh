@@ -28,6 +28,7 @@ struct GT { static constexpr int LOGB = 2, LEVELS = 25, DROP = 0; };        // (
 struct Tables {
     const uint2* tw1; const uint2* itw1;            // [1024] bit-reversed psi powers with Shoup companions
     const ulonglong2* tw2; const ulonglong2* itw2;  // [2048]
+    const double2* tw2d; const double2* itw2d;      // [2048] the same powers, centred, as (w, w/q2) doubles (FP64 path)
     const u32* lut1; const u64* lut2;               // test vectors (detector.rs:457-503)
     ulonglong2 n2_inv;                              // N2^-1 mod q2 (secret.rs:167-176), Shoup pair
     ulonglong2 r2;                                  // 2^64 mod q2, Shoup pair (undo REDC in the packing kernels)
@@ -57,6 +58,12 @@ template <class F, class G> __device__ __forceinline__ typename F::T gadget_digi
     constexpr S B = (S)1 << G::LOGB;
     S d = (r < G::LEVELS - 1) ? (((u >> (G::LOGB * r)) & (B - 1)) - (B >> 1)) : (u >> (G::LOGB * (G::LEVELS - 1)));
     return (T)((S)F::Q + d);
+}
+// digit r of offset word u as a small signed integer
+template <class F, class G> __device__ __forceinline__ int gadget_digit_signed(typename F::S u, int r) {
+    typedef typename F::S S;
+    constexpr S B = (S)1 << G::LOGB;
+    return (int)((r < G::LEVELS - 1) ? (((u >> (G::LOGB * r)) & (B - 1)) - (B >> 1)) : (u >> (G::LOGB * (G::LEVELS - 1))));
 }
 // centre x in (-2q, q) (a signed difference of two canonical values) to [-(q-1)/2, (q-1)/2]
 template <class F> __device__ __forceinline__ typename F::S centre_diff(typename F::S w) {
@@ -132,6 +139,58 @@ __device__ __forceinline__ void cmux_group(typename F::T* acc, typename F::T* wa
     group_sync<NT>(bar);
 }
 
+// ---- the same CMux step for level 2 with the transforms and the MAC on the FP64 pipe (see D2 in field.cuh) ------------
+// acc stays canonical u64 in shared memory (the decomposition is integer bit work); digits enter the NTT as doubles,
+// key words are centred doubles already multiplied by N^-1, the accumulators are 16 doubles instead of 16 x 128 bits.
+__device__ __forceinline__ void cmux_group_f64(u64* acc, double* wa, double* wb, int a, const double* __restrict__ key,
+                                               const Tables& tb, int t) {
+    typedef F2 F; typedef G2 G;
+    constexpr int N = F::N, NT = N / 8, L = G::LEVELS;
+    double ma[8], mb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ma[k] = 0.0; mb[k] = 0.0; }
+    int digit_count = 0;
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        const u64* ap = acc + p * N;
+        i64 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int pos = t + NT * k;
+            i64 w = rotated<F>(ap, pos, a) - (i64)ap[pos];
+            u[k] = gadget_word<F, G>(centre_diff<F>(w));
+        }
+#pragma unroll 1
+        for (int r = 0; r < L; ++r, ++digit_count) {
+            double x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r));
+            ntt_forward_regs_d(x, (digit_count & 1) ? wb : wa, tb.tw2d, t);
+            const double* ka = key + (size_t)(p * L + r) * 2 * N;
+            const double* kb = ka + N;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int idx = PassGeom<F, 3>::idx(t, k);
+                ma[k] = __dadd_rn(ma[k], D2::mulmod_key(x[k], __ldg(ka + idx)));      // 12 terms x 0.66q < 2^53
+                mb[k] = __dadd_rn(mb[k], D2::mulmod_key(x[k], __ldg(kb + idx)));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ma[k] = D2::renorm(ma[k]); mb[k] = D2::renorm(mb[k]); }
+    __syncthreads();
+    ntt_inverse_regs2_d(ma, mb, wa, wb, tb.itw2d, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int pos = t + NT * k;
+        i64 va = (i64)acc[pos] + D2::to_i64(ma[k]), vb = (i64)acc[N + pos] + D2::to_i64(mb[k]);
+        va += va < 0 ? (i64)F::Q : 0; va -= va >= (i64)F::Q ? (i64)F::Q : 0;
+        vb += vb < 0 ? (i64)F::Q : 0; vb -= vb >= (i64)F::Q ? (i64)F::Q : 0;
+        acc[pos] = (u64)va; acc[N + pos] = (u64)vb;
+    }
+    __syncthreads();
+}
+
 // acc = (0, LUT * X^(2N - b))  — start of BlindRotationKey::blind_rotate (detector.rs:555,623)
 template <class F> __device__ __forceinline__ void init_acc(typename F::T* acc, const typename F::T* __restrict__ lut, int b, int t) {
     typedef typename F::S S;
@@ -187,10 +246,10 @@ constexpr int L2_THREADS = 256;
 constexpr size_t L2_SMEM = (size_t)4 * F2::N * sizeof(u64) + 672 * sizeof(unsigned short);
 
 __global__ void __launch_bounds__(L2_THREADS, 2)
-l2_blind_rotate_kernel(const u32* __restrict__ lwe, const u64* __restrict__ bsk2, u64* __restrict__ out, Tables tb) {
+l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ bsk2, u64* __restrict__ out, Tables tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* acc = reinterpret_cast<u64*>(smem_raw);
-    u64* wa = acc + 2 * F2::N; u64* wb = wa + F2::N;
+    double* wa = reinterpret_cast<double*>(acc + 2 * F2::N); double* wb = wa + F2::N;
     unsigned short* la = reinterpret_cast<unsigned short*>(wb + F2::N);
     const int msg = blockIdx.x, t = threadIdx.x;
     for (int i = t; i < LWE2_STRIDE_IN; i += L2_THREADS) la[i] = (unsigned short)lwe[(size_t)msg * LWE2_STRIDE_IN + i];
@@ -200,7 +259,7 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const u64* __restrict__ bsk2
 #pragma unroll 1
     for (int i = 0; i < LWE2_N; ++i) {
         const int a = la[i];
-        if (a != 0) cmux_group<F2, G2>(acc, wa, wb, a, bsk2 + (size_t)i * 2 * G2::LEVELS * 2 * F2::N, tb, t, 0);
+        if (a != 0) cmux_group_f64(acc, wa, wb, a, bsk2 + (size_t)i * 2 * G2::LEVELS * 2 * F2::N, tb, t);
     }
     for (int e = t; e < 2 * F2::N; e += L2_THREADS) out[(size_t)msg * 2 * F2::N + e] = acc[e];
 }
@@ -480,6 +539,13 @@ template <class F>
 __global__ void scale_kernel(const typename F::T* __restrict__ in, typename F::T* __restrict__ out, size_t n, typename F::TW c) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = F::csub(F::mul_shoup(in[i], c), F::Q);
+}
+// FP64-path key form: word -> centred(word * c mod q2) as a double (c = N2^-1; exact, |value| <= q/2 < 2^53)
+__global__ void key_to_double_kernel(const u64* __restrict__ in, double* __restrict__ out, size_t n, ulonglong2 c) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 v = F2::csub(F2::mul_shoup(in[i], c), F2::Q);
+    out[i] = v > (Q2 >> 1) ? -(double)(i64)(Q2 - v) : (double)(i64)v;
 }
 __global__ void ksk_pad_kernel(const u32* __restrict__ in, u32* __restrict__ out, size_t rows) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

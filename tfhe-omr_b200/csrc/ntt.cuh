@@ -134,4 +134,82 @@ template <class F> __device__ __forceinline__ void ntt_inverse_regs2(typename F:
     pass_load<F, 0>(xa, wa, t); pass_load<F, 0>(xb, wb, t); inv_pass<F, 0>(xa, itw, t); inv_pass<F, 0>(xb, itw, t);
 }
 
+// ---- FP64 variants for level 2 (same pass geometry / swizzle as F2; elements are integer-valued doubles) ------------
+// Lazy-range schedule of the forward transform (T = mulmod output, |T| < 0.76q; growth 0.76q per stage):
+//   stages 0-5 from |x| <= 65 reach 4.56q (< 8q exact; mulmod inputs <= 3.8q), renormalise at the start of pass 2,
+//   stages 6-9 reach 3.54q, and the last stage renormalises its pass-through operand so outputs are <= 1.26q.
+template <int P> __device__ __forceinline__ void pass_load_d(double (&x)[8], const double* w, int t) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = w[swz(F2(), PassGeom<F2, P>::idx(t, k))];
+}
+template <int P> __device__ __forceinline__ void pass_store_d(const double (&x)[8], double* w, int t) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[swz(F2(), PassGeom<F2, P>::idx(t, k))] = x[k];
+}
+template <int P> __device__ __forceinline__ void fwd_pass_d(double (&x)[8], const double2* __restrict__ tw, int t) {
+    typedef PassGeom<F2, P> GEO;
+    if (P == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = D2::renorm(x[k]);
+    }
+#pragma unroll
+    for (int g = 0; g < GEO::G; ++g) {
+        const int j = GEO::block_of(t, g);
+#pragma unroll
+        for (int l = 0; l < GEO::NS; ++l) {
+            const int half = GEO::EP >> (l + 1);
+            const bool last = (GEO::S0 + l == F2::LOGN - 1);
+#pragma unroll
+            for (int sb = 0; sb < (1 << l); ++sb) {
+                const double2 w = __ldg(&tw[(1 << (GEO::S0 + l)) + (j << l) + sb]);
+#pragma unroll
+                for (int h = 0; h < half; ++h) {
+                    const int lo = g * GEO::EP + sb * 2 * half + h, hi = lo + half;
+                    const double u = last ? D2::renorm(x[lo]) : x[lo];
+                    const double v = D2::mulmod(x[hi], w.x, w.y);
+                    x[lo] = __dadd_rn(u, v); x[hi] = __dadd_rn(u, -v);
+                }
+            }
+        }
+    }
+}
+// inverse (Gentleman-Sande): inputs |x| < 0.76q; sums are renormalised, differences (< 1.52q) go through mulmod
+template <int P> __device__ __forceinline__ void inv_pass_d(double (&x)[8], const double2* __restrict__ itw, int t) {
+    typedef PassGeom<F2, P> GEO;
+#pragma unroll
+    for (int g = 0; g < GEO::G; ++g) {
+        const int j = GEO::block_of(t, g);
+#pragma unroll
+        for (int l = GEO::NS - 1; l >= 0; --l) {
+            const int half = GEO::EP >> (l + 1);
+#pragma unroll
+            for (int sb = 0; sb < (1 << l); ++sb) {
+                const double2 w = __ldg(&itw[(1 << (GEO::S0 + l)) + (j << l) + sb]);
+#pragma unroll
+                for (int h = 0; h < half; ++h) {
+                    const int lo = g * GEO::EP + sb * 2 * half + h, hi = lo + half;
+                    const double u = x[lo], v = x[hi];
+                    x[lo] = D2::renorm(__dadd_rn(u, v));
+                    x[hi] = D2::mulmod(__dadd_rn(u, -v), w.x, w.y);
+                }
+            }
+        }
+    }
+}
+__device__ __forceinline__ void ntt_forward_regs_d(double (&x)[8], double* w, const double2* __restrict__ tw, int t) {
+    fwd_pass_d<0>(x, tw, t); pass_store_d<0>(x, w, t); __syncthreads();
+    pass_load_d<1>(x, w, t); fwd_pass_d<1>(x, tw, t); pass_store_d<1>(x, w, t); __syncthreads();
+    pass_load_d<2>(x, w, t); fwd_pass_d<2>(x, tw, t); pass_store_d<2>(x, w, t); __syncthreads();
+    pass_load_d<3>(x, w, t); fwd_pass_d<3>(x, tw, t);
+}
+__device__ __forceinline__ void ntt_inverse_regs2_d(double (&xa)[8], double (&xb)[8], double* wa, double* wb,
+                                                    const double2* __restrict__ itw, int t) {
+    inv_pass_d<3>(xa, itw, t); inv_pass_d<3>(xb, itw, t); pass_store_d<3>(xa, wa, t); pass_store_d<3>(xb, wb, t); __syncthreads();
+    pass_load_d<2>(xa, wa, t); pass_load_d<2>(xb, wb, t); inv_pass_d<2>(xa, itw, t); inv_pass_d<2>(xb, itw, t);
+    pass_store_d<2>(xa, wa, t); pass_store_d<2>(xb, wb, t); __syncthreads();
+    pass_load_d<1>(xa, wa, t); pass_load_d<1>(xb, wb, t); inv_pass_d<1>(xa, itw, t); inv_pass_d<1>(xb, itw, t);
+    pass_store_d<1>(xa, wa, t); pass_store_d<1>(xb, wb, t); __syncthreads();
+    pass_load_d<0>(xa, wa, t); pass_load_d<0>(xb, wb, t); inv_pass_d<0>(xa, itw, t); inv_pass_d<0>(xb, itw, t);
+}
+
 }  // namespace omr
