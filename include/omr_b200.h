@@ -136,7 +136,8 @@ int omr_ntt_forward_device(omr_ctx* ctx, int level, void* d_data, size_t batch, 
 int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d_data, size_t batch, void* stream);
 
 /* Step-0 peak: sustained rate of the register-only Shoup butterfly loop the NTTs are made of,
- * level 1 = 32-bit (q1), level 2 = 64-bit (q2); the denominator of the integer-pipe roofline in bench.py. */
+ * level 1 = 32-bit integer (q1), level 2 = 64-bit integer (q2), level 3 = q2 on the FP64 pipe (what the level-2 kernel
+ * uses); the denominators of the compute roofline in bench.py. */
 int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_second);
 
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */

@@ -282,14 +282,14 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     {
         const u32 c1 = h_mulmod<u32>((u32)(((u64)1 << 32) % Q1), n1i, Q1);
         CKC(cudaMemcpyAsync(ctx->bsk1, keys->bsk1, n_bsk1 * 4, kind, s));
-        if (coeff) { ntt_kernel<F1, false><<<(unsigned)(n_bsk1 / F1::N), F1::N / 8, F1::N * 4, s>>>(ctx->bsk1, tb, ctx->n1_inv); ++ctx->launches; }
+        if (coeff) { ntt_kernel<F1, false><<<(unsigned)(n_bsk1 / F1::N), ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>(ctx->bsk1, tb, ctx->n1_inv); ++ctx->launches; }
         scale_kernel<F1><<<(unsigned)((n_bsk1 + 255) / 256), 256, 0, s>>>(ctx->bsk1, ctx->bsk1, n_bsk1, make_uint2(c1, h_shoup<u32>(c1, Q1))); ++ctx->launches;
         const u64 c2 = h_mulmod<u64>(r2, n2i, Q2); const ulonglong2 c2s = make_ulonglong2(c2, h_shoup<u64>(c2, Q2));
         CKC(cudaMemcpyAsync(ctx->bsk2, keys->bsk2, n_bsk2 * 8, kind, s));
-        if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_bsk2 / F2::N), F2::N / 8, F2::N * 8, s>>>(ctx->bsk2, tb, ctx->n2_inv); ++ctx->launches; }
+        if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_bsk2 / F2::N), ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ctx->bsk2, tb, ctx->n2_inv); ++ctx->launches; }
         key_to_double_kernel<<<(unsigned)((n_bsk2 + 255) / 256), 256, 0, s>>>(ctx->bsk2, reinterpret_cast<double*>(ctx->bsk2), n_bsk2, ctx->n2_inv); ++ctx->launches;
         CKC(cudaMemcpyAsync(ctx->trk, keys->trace, n_trk * 8, kind, s));
-        if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_trk / F2::N), F2::N / 8, F2::N * 8, s>>>(ctx->trk, tb, ctx->n2_inv); ++ctx->launches; }
+        if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_trk / F2::N), ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ctx->trk, tb, ctx->n2_inv); ++ctx->launches; }
         scale_kernel<F2><<<(unsigned)((n_trk + 255) / 256), 256, 0, s>>>(ctx->trk, ctx->trk, n_trk, c2s); ++ctx->launches;
         CKC(cudaGetLastError());
         CKC(cudaStreamSynchronize(s));
@@ -370,8 +370,8 @@ int omr_ntt_forward_device(omr_ctx* ctx, int level, void* d, size_t batch, void*
     std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     if (!batch) return OMR_OK;
-    if (level == 1) ntt_kernel<F1, false><<<(unsigned)batch, F1::N / 8, F1::N * 4, s>>>((u32*)d, ctx->tb, ctx->n1_inv);
-    else ntt_kernel<F2, false><<<(unsigned)batch, F2::N / 8, F2::N * 8, s>>>((u64*)d, ctx->tb, ctx->n2_inv);
+    if (level == 1) ntt_kernel<F1, false><<<(unsigned)batch, ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>((u32*)d, ctx->tb, ctx->n1_inv);
+    else ntt_kernel<F2, false><<<(unsigned)batch, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>((u64*)d, ctx->tb, ctx->n2_inv);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
@@ -380,8 +380,8 @@ int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d, size_t batch, void*
     std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     if (!batch) return OMR_OK;
-    if (level == 1) ntt_kernel<F1, true><<<(unsigned)batch, F1::N / 8, F1::N * 4, s>>>((u32*)d, ctx->tb, ctx->n1_inv);
-    else ntt_kernel<F2, true><<<(unsigned)batch, F2::N / 8, F2::N * 8, s>>>((u64*)d, ctx->tb, ctx->n2_inv);
+    if (level == 1) ntt_kernel<F1, true><<<(unsigned)batch, ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>((u32*)d, ctx->tb, ctx->n1_inv);
+    else ntt_kernel<F2, true><<<(unsigned)batch, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>((u64*)d, ctx->tb, ctx->n2_inv);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
@@ -504,7 +504,7 @@ int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, co
 }
 
 int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_second) {
-    if (!ctx || !mulmods_per_second || (level != 1 && level != 2) || iters <= 0) return OMR_ERR_INVALID;
+    if (!ctx || !mulmods_per_second || level < 1 || level > 3 || iters <= 0) return OMR_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
     const int blocks = prop.multiProcessorCount * 8, threads = 256;
@@ -513,7 +513,8 @@ int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_seco
     for (int rep = 0; rep < 2; ++rep) {          // first run warms up
         CK(cudaEventRecord(ctx->ev[0], s));
         if (level == 1) mulmod_peak_kernel<F1><<<blocks, threads, 0, s>>>((u32*)ctx->s_digest, ctx->n1_inv, iters);
-        else mulmod_peak_kernel<F2><<<blocks, threads, 0, s>>>((u64*)ctx->s_digest, ctx->n2_inv, iters);
+        else if (level == 2) mulmod_peak_kernel<F2><<<blocks, threads, 0, s>>>((u64*)ctx->s_digest, ctx->n2_inv, iters);
+        else mulmod_peak_f64_kernel<<<blocks, threads, 0, s>>>((double*)ctx->s_digest, make_double2(123456789012345.0, 123456789012345.0 / 1125899906826241.0), iters);
         ++ctx->launches; CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[1], s)); CK(cudaEventSynchronize(ctx->ev[1]));
     }

@@ -1,11 +1,11 @@
 // kernels.cuh — sm_100a kernels of the InstantOMR detection hot path.
 //   K1 l1_blind_rotate_kernel    detector.rs:505-531, 553-557   7 blind rotations over R_q1 + sum
 //   K2 keyswitch_kernel          detector.rs:560-596            sample extract, LWE key switch, mod switch, offset
-//   K3 l2_blind_rotate_kernel    detector.rs:599-624            blind rotation over R_q2
+//   K3 l2_blind_rotate_kernel    detector.rs:599-624            blind rotation over R_q2 (FP64 pipe, exact)
 //   K4 trace_kernel              detector.rs:626-639            *N^-1, homomorphic trace, to NTT form
 //   K5 pack_kernel<INDICES>      detector.rs:223-339            index digest
 //   K6 pack_kernel<PAYLOADS>     detector.rs:341-453            payload digest
-// plus partial-sum reduction, batched standalone NTTs and the key pre-transform.
+// plus partial-sum reduction, batched standalone NTTs and the key pre-transforms.
 // Tensor cores are deliberately unused: the contraction here is an exact modular NTT, not a floating-point GEMM.
 #pragma once
 #include "ntt.cuh"
@@ -35,13 +35,6 @@ struct Tables {
     u32 trace_dinv[TR_STEPS];                       // (2^k+1)^-1 mod 2*N2, k = 11..1
 };
 
-template <class F> __device__ __forceinline__ const typename F::TW* fwd_tw(const Tables& tb);
-template <> __device__ __forceinline__ const uint2* fwd_tw<F1>(const Tables& tb) { return tb.tw1; }
-template <> __device__ __forceinline__ const ulonglong2* fwd_tw<F2>(const Tables& tb) { return tb.tw2; }
-template <class F> __device__ __forceinline__ const typename F::TW* inv_tw(const Tables& tb);
-template <> __device__ __forceinline__ const uint2* inv_tw<F1>(const Tables& tb) { return tb.itw1; }
-template <> __device__ __forceinline__ const ulonglong2* inv_tw<F2>(const Tables& tb) { return tb.itw2; }
-
 // ---- signed gadget decomposition --------------------------------------------------------------------
 // offset word: u = round(v / 2^DROP) + SUM_{j<L-1} (B/2) B^j ; digit j<L-1 = ((u >> wj) & (B-1)) - B/2 ; top = u >> w(L-1)
 template <class F, class G> __device__ __forceinline__ typename F::S gadget_word(typename F::S v) {
@@ -52,18 +45,15 @@ template <class F, class G> __device__ __forceinline__ typename F::S gadget_word
     if (G::DROP > 0) v = (v + ((S)1 << (G::DROP > 0 ? G::DROP - 1 : 0))) >> G::DROP;
     return v + c;
 }
-// digit r of offset word u as a lazy field element in (0, 2q)
-template <class F, class G> __device__ __forceinline__ typename F::T gadget_digit(typename F::S u, int r) {
-    typedef typename F::S S; typedef typename F::T T;
-    constexpr S B = (S)1 << G::LOGB;
-    S d = (r < G::LEVELS - 1) ? (((u >> (G::LOGB * r)) & (B - 1)) - (B >> 1)) : (u >> (G::LOGB * (G::LEVELS - 1)));
-    return (T)((S)F::Q + d);
-}
 // digit r of offset word u as a small signed integer
 template <class F, class G> __device__ __forceinline__ int gadget_digit_signed(typename F::S u, int r) {
     typedef typename F::S S;
     constexpr S B = (S)1 << G::LOGB;
     return (int)((r < G::LEVELS - 1) ? (((u >> (G::LOGB * r)) & (B - 1)) - (B >> 1)) : (u >> (G::LOGB * (G::LEVELS - 1))));
+}
+// ... and as a lazy field element in (0, 2q)
+template <class F, class G> __device__ __forceinline__ typename F::T gadget_digit(typename F::S u, int r) {
+    return (typename F::T)((typename F::S)F::Q + (typename F::S)gadget_digit_signed<F, G>(u, r));
 }
 // centre x in (-2q, q) (a signed difference of two canonical values) to [-(q-1)/2, (q-1)/2]
 template <class F> __device__ __forceinline__ typename F::S centre_diff(typename F::S w) {
@@ -74,7 +64,6 @@ template <class F> __device__ __forceinline__ typename F::S centre_diff(typename
     if (w > H) w -= Q;
     return w;
 }
-
 // value of (X^a * p)[pos] for a in [0, 2N): signed (negated when the rotation wraps an odd number of times)
 template <class F> __device__ __forceinline__ typename F::S rotated(const typename F::T* p, int pos, int a) {
     typedef typename F::S S;
@@ -84,184 +73,219 @@ template <class F> __device__ __forceinline__ typename F::S rotated(const typena
     S r = (S)p[s];
     return neg ? -r : r;
 }
-
-// ---- one CMux step by a group of NT threads:  acc += ((X^a - 1) acc) [x] RGSW    -------------
-// acc: [2][N] canonical, shared memory.  wa, wb: exchange buffers.  key: [2L][2][N] in global memory, each word
-// pre-multiplied by R * N^-1 (R = 2^32 / 2^64) so that REDC of the MAC and the unscaled INTT give the exact product.
-template <class F, class G>
-__device__ __forceinline__ void cmux_group(typename F::T* acc, typename F::T* wa, typename F::T* wb, int a,
-                                           const typename F::T* __restrict__ key, const Tables& tb, int t, int bar) {
-    typedef typename F::T T; typedef typename F::S S; typedef typename F::Acc Acc;
-    constexpr int N = F::N, NT = N / 8, L = G::LEVELS;
-    const typename F::TW* tw = fwd_tw<F>(tb);
-    Acc ma[8], mb[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { ma[k] = Acc(); mb[k] = Acc(); }
-    int digit_count = 0;
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) {
-        const T* ap = acc + p * N;
-        S u[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int pos = t + NT * k;
-            S w = rotated<F>(ap, pos, a) - (S)ap[pos];
-            u[k] = gadget_word<F, G>(centre_diff<F>(w));
-        }
-#pragma unroll 1
-        for (int r = 0; r < L; ++r, ++digit_count) {
-            T x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = gadget_digit<F, G>(u[k], r);
-            T* w = (digit_count & 1) ? wb : wa;
-            ntt_forward_regs<F>(x, w, tw, t, bar);
-            const T* ka = key + (size_t)(p * L + r) * 2 * N;
-            const T* kb = ka + N;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int idx = PassGeom<F, 3>::idx(t, k);
-                F::mac(ma[k], x[k], __ldg(ka + idx));
-                F::mac(mb[k], x[k], __ldg(kb + idx));
-            }
-        }
-    }
-    T ya[8], yb[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { ya[k] = F::inv_prepare(F::redc(ma[k])); yb[k] = F::inv_prepare(F::redc(mb[k])); }
-    group_sync<NT>(bar);                              // last forward pass-3 loads done before wa/wb are reused
-    ntt_inverse_regs2<F>(ya, yb, wa, wb, inv_tw<F>(tb), t, bar);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int pos = t + NT * k;
-        acc[pos] = F::add_canon(acc[pos], ya[k]);
-        acc[N + pos] = F::add_canon(acc[N + pos], yb[k]);
-    }
-    group_sync<NT>(bar);
-}
-
-// ---- the same CMux step for level 2 with the transforms and the MAC on the FP64 pipe (see D2 in field.cuh) ------------
-// acc stays canonical u64 in shared memory (the decomposition is integer bit work); digits enter the NTT as doubles,
-// key words are centred doubles already multiplied by N^-1, the accumulators are 16 doubles instead of 16 x 128 bits.
-__device__ __forceinline__ void cmux_group_f64(u64* acc, double* wa, double* wb, int a, const double* __restrict__ key,
-                                               const Tables& tb, int t) {
-    typedef F2 F; typedef G2 G;
-    constexpr int N = F::N, NT = N / 8, L = G::LEVELS;
-    double ma[8], mb[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { ma[k] = 0.0; mb[k] = 0.0; }
-    int digit_count = 0;
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) {
-        const u64* ap = acc + p * N;
-        i64 u[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int pos = t + NT * k;
-            i64 w = rotated<F>(ap, pos, a) - (i64)ap[pos];
-            u[k] = gadget_word<F, G>(centre_diff<F>(w));
-        }
-#pragma unroll 1
-        for (int r = 0; r < L; ++r, ++digit_count) {
-            double x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r));
-            ntt_forward_regs_d(x, (digit_count & 1) ? wb : wa, tb.tw2d, t);
-            const double* ka = key + (size_t)(p * L + r) * 2 * N;
-            const double* kb = ka + N;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int idx = PassGeom<F, 3>::idx(t, k);
-                ma[k] = __dadd_rn(ma[k], D2::mulmod_key(x[k], __ldg(ka + idx)));      // 12 terms x 0.66q < 2^53
-                mb[k] = __dadd_rn(mb[k], D2::mulmod_key(x[k], __ldg(kb + idx)));
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { ma[k] = D2::renorm(ma[k]); mb[k] = D2::renorm(mb[k]); }
-    __syncthreads();
-    ntt_inverse_regs2_d(ma, mb, wa, wb, tb.itw2d, t);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int pos = t + NT * k;
-        i64 va = (i64)acc[pos] + D2::to_i64(ma[k]), vb = (i64)acc[N + pos] + D2::to_i64(mb[k]);
-        va += va < 0 ? (i64)F::Q : 0; va -= va >= (i64)F::Q ? (i64)F::Q : 0;
-        vb += vb < 0 ? (i64)F::Q : 0; vb -= vb >= (i64)F::Q ? (i64)F::Q : 0;
-        acc[pos] = (u64)va; acc[N + pos] = (u64)vb;
-    }
-    __syncthreads();
-}
-
-// acc = (0, LUT * X^(2N - b))  — start of BlindRotationKey::blind_rotate (detector.rs:555,623)
-template <class F> __device__ __forceinline__ void init_acc(typename F::T* acc, const typename F::T* __restrict__ lut, int b, int t) {
+// offset words of ((X^a - 1) * p) at the pass-0 positions of thread t
+template <class F, class G, class GEO> __device__ __forceinline__ void decompose_words(typename F::S (&u)[GEO::E], const typename F::T* p, int a, int t) {
     typedef typename F::S S;
-    constexpr int N = F::N, NT = N / 8;
+#pragma unroll
+    for (int k = 0; k < GEO::E; ++k) {
+        const int pos = t + GEO::NT * k;
+        u[k] = gadget_word<F, G>(centre_diff<F>(rotated<F>(p, pos, a) - (S)p[pos]));
+    }
+}
+// acc = (0, LUT * X^(2N - b))  — start of BlindRotationKey::blind_rotate (detector.rs:555,623)
+template <class F, class GEO> __device__ __forceinline__ void init_acc(typename F::T* acc, const typename F::T* __restrict__ lut, int b, int t) {
+    typedef typename F::S S;
+    constexpr int N = F::N;
     const int rot = (2 * N - b) % (2 * N);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int pos = t + NT * k;
+    for (int k = 0; k < GEO::E; ++k) {
+        const int pos = t + GEO::NT * k;
         S v = rotated<F>(lut, pos, rot);
         acc[pos] = 0;
         acc[N + pos] = (typename F::T)(v < 0 ? v + (S)F::Q : v);
     }
 }
 
+// ---- TMA (cp.async.bulk) + mbarrier helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra LAB_DONE;\n bra LAB_WAIT;\n LAB_DONE:\n }\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// one elected thread: bulk copy `bytes` (multiple of 16) global -> shared, completion signalled on `bar`
+__device__ __forceinline__ void tma_load(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---- K1: first-level blind rotations + sum -----------------------------------------------------------------------
-// one CTA per message, 7 groups of 128 threads (one per clue), each with its own accumulator; groups synchronise
-// with named barriers only.  clue extraction (CmLwe::extract_all, detector.rs:514) is index arithmetic on the fly.
-constexpr int L1_THREADS = CLUE_COUNT * 128;
-constexpr size_t L1_SMEM = (size_t)CLUE_COUNT * 4 * F1::N * sizeof(u32) + CLUE_N * sizeof(unsigned short) + 16;
+// One CTA per message: 7 groups of 64 threads (one per clue), 16 coefficients per thread, each group with its own
+// accumulator and exchange buffers (named barriers only inside the loop body).  Per CMux step the 64 KiB RGSW tile
+// BSK1[i] is staged ONCE into shared memory by a TMA bulk copy and reused by all 7 clues; the copy of tile i+1 is in
+// flight while the groups run their inverse transforms and the first forward transform of the next step.  Twiddles
+// live in shared memory.  clue extraction (CmLwe::extract_all, detector.rs:514) is index arithmetic on the fly.
+constexpr int L1_GROUP = GeoL1::NT;                        // 64
+constexpr int L1_THREADS = CLUE_COUNT * L1_GROUP;          // 448
+constexpr int L1_TILE_WORDS = 2 * G1::LEVELS * 2 * F1::N;  // 16384 u32 = 64 KiB
+constexpr int L1_GROUP_WORDS = 2 * F1::N + 2 * GeoL1::BUF;
+constexpr size_t L1_SMEM = 128 /*align*/ + (size_t)L1_TILE_WORDS * 4 + 2 * F1::N * sizeof(uint2) + (size_t)CLUE_COUNT * L1_GROUP_WORDS * 4 +
+                           CLUE_N * sizeof(unsigned short) + 16;
 
 __global__ void __launch_bounds__(L1_THREADS, 1)
 l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned short* __restrict__ clue_b,
                        const u32* __restrict__ bsk1, u32* __restrict__ out, Tables tb) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u32* smem = reinterpret_cast<u32*>(smem_raw);
-    const int msg = blockIdx.x, c = threadIdx.x >> 7, t = threadIdx.x & 127;
-    u32* acc = smem + (size_t)c * 4 * F1::N;      // [2][N]
-    u32* wa = acc + 2 * F1::N; u32* wb = wa + F1::N;
-    unsigned short* ca = reinterpret_cast<unsigned short*>(smem + (size_t)CLUE_COUNT * 4 * F1::N);
+    typedef F1 F; typedef G1 G; typedef GeoL1 GEO; typedef ArInt<F1> AR;
+    constexpr int N = F::N, E = GEO::E, L = G::LEVELS;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* sp = reinterpret_cast<unsigned char*>(((size_t)smem_dyn + 127) & ~(size_t)127);
+    u32* ktile = reinterpret_cast<u32*>(sp); sp += (size_t)L1_TILE_WORDS * 4;
+    uint2* s_tw = reinterpret_cast<uint2*>(sp); sp += N * sizeof(uint2);
+    uint2* s_itw = reinterpret_cast<uint2*>(sp); sp += N * sizeof(uint2);
+    u32* groups = reinterpret_cast<u32*>(sp); sp += (size_t)CLUE_COUNT * L1_GROUP_WORDS * 4;
+    unsigned short* ca = reinterpret_cast<unsigned short*>(sp); sp += CLUE_N * sizeof(unsigned short);
+    u64* mbar = reinterpret_cast<u64*>(((size_t)sp + 7) & ~(size_t)7);
+
+    const int msg = blockIdx.x, c = threadIdx.x / L1_GROUP, t = threadIdx.x % L1_GROUP;
+    u32* acc = groups + (size_t)c * L1_GROUP_WORDS;       // [2][N]
+    ExBuf<u32> eb{acc + 2 * N, acc + 2 * N + GEO::BUF};
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    for (int i = threadIdx.x; i < N; i += L1_THREADS) { s_tw[i] = tb.tw1[i]; s_itw[i] = tb.itw1[i]; }
     for (int i = threadIdx.x; i < CLUE_N; i += L1_THREADS) ca[i] = clue_a[(size_t)msg * CLUE_N + i];
-    const int b = clue_b[(size_t)msg * CLUE_COUNT + c];
-    init_acc<F1>(acc, tb.lut1, b, t);
+    init_acc<F, GEO>(acc, tb.lut1, clue_b[(size_t)msg * CLUE_COUNT + c], t);
     __syncthreads();
+    if (threadIdx.x == 0) tma_load(ktile, bsk1, L1_TILE_WORDS * 4, mbar);
     const int bar = 1 + c;
 #pragma unroll 1
     for (int i = 0; i < CLUE_N; ++i) {
-        // a^(c)_i = a_{c-i} (i <= c), -a_{512+c-i} (i > c)   SURVEY A.3
+        // a^(c)_i = a_{c-i} (i <= c), -a_{512+c-i} (i > c)   SURVEY A.3.   a == 0 is not skipped: (X^0 - 1) acc = 0
+        // decomposes to all-zero digits and adds nothing, bit-identical to skipping (keeps the groups in lock step).
         const int a = i <= c ? ca[c - i] : ((CLUE_Q - ca[CLUE_N + c - i]) & (CLUE_Q - 1));
-        if (a != 0) cmux_group<F1, G1>(acc, wa, wb, a, bsk1 + (size_t)i * 2 * G1::LEVELS * 2 * F1::N, tb, t, bar);
+        u64 ma[E], mb[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) { ma[k] = 0; mb[k] = 0; }
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            i32 u[E];
+            decompose_words<F, G, GEO>(u, acc + p * N, a, t);
+#pragma unroll 1
+            for (int r = 0; r < L; ++r) {
+                u32 x[E];
+#pragma unroll
+                for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, G>(u[k], r);
+                ntt_forward<AR, GEO, LdShared>(x, eb, s_tw, t, bar);
+                if (p == 0 && r == 0) mbar_wait(mbar, i & 1);                    // RGSW tile i has landed
+                const u32* ka = ktile + (size_t)(p * L + r) * 2 * N + out_idx<GEO>(t, 0);
+                const u32* kb = ka + N;
+#pragma unroll
+                for (int k = 0; k < E; k += 4) {
+                    const int o = out_idx<GEO>(0, k) - out_idx<GEO>(0, 0);
+                    const uint4 va = *reinterpret_cast<const uint4*>(ka + o), vb = *reinterpret_cast<const uint4*>(kb + o);
+                    F::mac(ma[k], x[k], va.x); F::mac(ma[k + 1], x[k + 1], va.y); F::mac(ma[k + 2], x[k + 2], va.z); F::mac(ma[k + 3], x[k + 3], va.w);
+                    F::mac(mb[k], x[k], vb.x); F::mac(mb[k + 1], x[k + 1], vb.y); F::mac(mb[k + 2], x[k + 2], vb.z); F::mac(mb[k + 3], x[k + 3], vb.w);
+                }
+            }
+        }
+        u32 ya[E], yb[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) { ya[k] = F::inv_prepare(F::redc(ma[k])); yb[k] = F::inv_prepare(F::redc(mb[k])); }
+        __syncthreads();                                                         // every clue is done with tile i
+        if (threadIdx.x == 0 && i + 1 < CLUE_N) tma_load(ktile, bsk1 + (size_t)(i + 1) * L1_TILE_WORDS, L1_TILE_WORDS * 4, mbar);
+        ntt_inverse<AR, GEO, LdShared>(ya, eb, s_itw, t, bar);
+        ntt_inverse<AR, GEO, LdShared>(yb, eb, s_itw, t, bar);
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const int pos = t + GEO::NT * k;
+            acc[pos] = F::add_canon(acc[pos], ya[k]);
+            acc[N + pos] = F::add_canon(acc[N + pos], yb[k]);
+        }
+        group_sync<GEO::NT>(bar);
     }
     __syncthreads();
     // sum of the 7 accumulators (add_element_wise, detector.rs:556)
-    for (int e = threadIdx.x; e < 2 * F1::N; e += L1_THREADS) {
+    for (int e = threadIdx.x; e < 2 * N; e += L1_THREADS) {
         u32 s = 0;
 #pragma unroll
-        for (int cc = 0; cc < CLUE_COUNT; ++cc) s += smem[(size_t)cc * 4 * F1::N + e];    // 7q < 2^30
-        out[(size_t)msg * 2 * F1::N + e] = s % Q1;
+        for (int cc = 0; cc < CLUE_COUNT; ++cc) s += groups[(size_t)cc * L1_GROUP_WORDS + e];    // 7q < 2^30
+        out[(size_t)msg * 2 * N + e] = s % Q1;
     }
 }
 
-// ---- K3: second-level blind rotation ------------------------------------------------------------------------------
-constexpr int L2_THREADS = 256;
-constexpr size_t L2_SMEM = (size_t)4 * F2::N * sizeof(u64) + 672 * sizeof(unsigned short);
+// ---- K3: second-level blind rotation, transforms and MAC on the FP64 pipe (D2 in field.cuh) -----------------------------
+// One CTA (256 threads, 8 coefficients each) per message.  acc stays canonical u64 in shared memory (decomposition is
+// integer bit work); digits enter the NTT as doubles, two digits per pass (shared barriers, twice the ILP); key words are
+// centred doubles already multiplied by N^-1, streamed from L2 with L1::no_allocate so the twiddle tables stay in L1;
+// the MAC accumulators are 16 doubles.
+constexpr int L2_THREADS = GeoL2::NT;
+constexpr size_t L2_SMEM = (size_t)2 * F2::N * 8 + (size_t)4 * GeoL2::BUF * 8 + 672 * sizeof(unsigned short);
+
+__device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 
 __global__ void __launch_bounds__(L2_THREADS, 2)
 l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ bsk2, u64* __restrict__ out, Tables tb) {
+    typedef F2 F; typedef G2 G; typedef GeoL2 GEO; typedef ArD2 AR;
+    constexpr int N = F::N, E = GEO::E, L = G::LEVELS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* acc = reinterpret_cast<u64*>(smem_raw);
-    double* wa = reinterpret_cast<double*>(acc + 2 * F2::N); double* wb = wa + F2::N;
-    unsigned short* la = reinterpret_cast<unsigned short*>(wb + F2::N);
+    double* bufs = reinterpret_cast<double*>(acc + 2 * N);
+    ExBuf<double> e0{bufs, bufs + GEO::BUF}, e1{bufs + 2 * GEO::BUF, bufs + 3 * GEO::BUF};
+    unsigned short* la = reinterpret_cast<unsigned short*>(bufs + 4 * GEO::BUF);
     const int msg = blockIdx.x, t = threadIdx.x;
     for (int i = t; i < LWE2_STRIDE_IN; i += L2_THREADS) la[i] = (unsigned short)lwe[(size_t)msg * LWE2_STRIDE_IN + i];
     __syncthreads();
-    init_acc<F2>(acc, tb.lut2, la[LWE2_N], t);
+    init_acc<F, GEO>(acc, tb.lut2, la[LWE2_N], t);
     __syncthreads();
 #pragma unroll 1
     for (int i = 0; i < LWE2_N; ++i) {
         const int a = la[i];
-        if (a != 0) cmux_group_f64(acc, wa, wb, a, bsk2 + (size_t)i * 2 * G2::LEVELS * 2 * F2::N, tb, t);
+        if (a == 0) continue;                                  // CTA-uniform: (X^0 - 1) acc = 0 adds nothing
+        const double* key = bsk2 + (size_t)i * 2 * L * 2 * N + out_idx<GEO>(t, 0);
+        double ma[E], mb[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) { ma[k] = 0.0; mb[k] = 0.0; }
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            i64 u[E];
+            decompose_words<F, G, GEO>(u, acc + p * N, a, t);
+#pragma unroll 1
+            for (int r = 0; r < L; r += 2) {
+                double x[E], y[E];
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r));
+                    y[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r + 1));
+                }
+                ntt_forward2<AR, GEO, LdGlobal>(x, y, e0, e1, tb.tw2d, t, 0);
+                const double* kx = key + (size_t)(p * L + r) * 2 * N;         // rows r and r+1: [a | b] each
+#pragma unroll
+                for (int k = 0; k < E; k += 2) {
+                    const int o = out_idx<GEO>(0, k) - out_idx<GEO>(0, 0);
+                    const double2 xa = ld_stream_f64x2(kx + o), xb = ld_stream_f64x2(kx + N + o);
+                    const double2 ya = ld_stream_f64x2(kx + 2 * N + o), yb = ld_stream_f64x2(kx + 3 * N + o);
+                    // 12 terms x 0.66q < 2^53: the running sums stay exact
+                    ma[k] = __dadd_rn(ma[k], __dadd_rn(D2::mulmod_key(x[k], xa.x), D2::mulmod_key(y[k], ya.x)));
+                    ma[k + 1] = __dadd_rn(ma[k + 1], __dadd_rn(D2::mulmod_key(x[k + 1], xa.y), D2::mulmod_key(y[k + 1], ya.y)));
+                    mb[k] = __dadd_rn(mb[k], __dadd_rn(D2::mulmod_key(x[k], xb.x), D2::mulmod_key(y[k], yb.x)));
+                    mb[k + 1] = __dadd_rn(mb[k + 1], __dadd_rn(D2::mulmod_key(x[k + 1], xb.y), D2::mulmod_key(y[k + 1], yb.y)));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < E; ++k) { ma[k] = D2::renorm(ma[k]); mb[k] = D2::renorm(mb[k]); }
+        ntt_inverse2<AR, GEO, LdGlobal>(ma, mb, e0, e1, tb.itw2d, t, 0);
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const int pos = t + GEO::NT * k;
+            i64 va = (i64)acc[pos] + D2::to_i64(ma[k]), vb = (i64)acc[N + pos] + D2::to_i64(mb[k]);
+            va += va < 0 ? (i64)F::Q : 0; va -= va >= (i64)F::Q ? (i64)F::Q : 0;
+            vb += vb < 0 ? (i64)F::Q : 0; vb -= vb >= (i64)F::Q ? (i64)F::Q : 0;
+            acc[pos] = (u64)va; acc[N + pos] = (u64)vb;
+        }
+        __syncthreads();
     }
-    for (int e = t; e < 2 * F2::N; e += L2_THREADS) out[(size_t)msg * 2 * F2::N + e] = acc[e];
+    for (int e = t; e < 2 * N; e += L2_THREADS) out[(size_t)msg * 2 * N + e] = acc[e];
 }
 
 // ---- K2: sample extraction + LWE key switch + modulus switch + offset ---------------------------------------------
@@ -320,9 +344,9 @@ keyswitch_kernel(const u32* __restrict__ rlwe, const u32* __restrict__ ksk, u32*
     }
 }
 
-// ---- K4: scale by N^-1, homomorphic trace, forward NTT ------------------------------------------------------------
-constexpr int TR_THREADS = 256;
-constexpr size_t TR_SMEM = (size_t)4 * F2::N * sizeof(u64);
+// ---- K4: scale by N^-1, homomorphic trace, forward NTT (integer F2 arithmetic) ----------------------------------------
+constexpr int TR_THREADS = GeoL2::NT;
+constexpr size_t TR_SMEM = (size_t)2 * F2::N * 8 + (size_t)4 * GeoL2::BUF * 8;
 
 // sigma_d(p)[pos] as a signed value: source index i0 = pos * d^-1 mod 2N
 __device__ __forceinline__ i64 automorphed(const u64* p, int pos, u32 dinv) {
@@ -332,11 +356,12 @@ __device__ __forceinline__ i64 automorphed(const u64* p, int pos, u32 dinv) {
 
 __global__ void __launch_bounds__(TR_THREADS, 2)
 trace_kernel(u64* __restrict__ ct, const u64* __restrict__ trk, Tables tb) {
+    typedef F2 F; typedef F::Acc Acc; typedef GeoL2 GEO; typedef ArInt<F2> AR;
+    constexpr int N = F::N, E = GEO::E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* acc = reinterpret_cast<u64*>(smem_raw);        // [2][N]: a, b
-    u64* wa = acc + 2 * F2::N; u64* wb = wa + F2::N;
-    typedef F2 F; typedef F::Acc Acc;
-    constexpr int N = F::N, NT = N / 8;
+    u64* bufs = acc + 2 * N;
+    ExBuf<u64> e0{bufs, bufs + GEO::BUF}, e1{bufs + 2 * GEO::BUF, bufs + 3 * GEO::BUF};
     const int t = threadIdx.x;
     u64* g = ct + (size_t)blockIdx.x * 2 * N;
     for (int e = t; e < 2 * N; e += TR_THREADS) acc[e] = F::csub(F::mul_shoup(g[e], tb.n2_inv), F::Q);   // detector.rs:635-636
@@ -344,61 +369,57 @@ trace_kernel(u64* __restrict__ ct, const u64* __restrict__ trk, Tables tb) {
 #pragma unroll 1
     for (int step = 0; step < TR_STEPS; ++step) {
         const u32 dinv = tb.trace_dinv[step];
-        i64 u[8];
+        i64 u[E];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            i64 v = automorphed(acc, t + NT * k, dinv);              // in (-q, q)
+        for (int k = 0; k < E; ++k) {
+            i64 v = automorphed(acc, t + GEO::NT * k, dinv);              // in (-q, q)
             constexpr i64 H = (i64)(F::Q >> 1);
             if (v > H) v -= (i64)F::Q;
             if (v < -H) v += (i64)F::Q;
             u[k] = gadget_word<F, GT>(v);
         }
-        Acc ma[8], mb[8];
+        Acc ma[E], mb[E];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { ma[k] = Acc(); mb[k] = Acc(); }
+        for (int k = 0; k < E; ++k) { ma[k] = Acc(); mb[k] = Acc(); }
         const u64* key = trk + (size_t)step * TR_LEVELS * 2 * N;
 #pragma unroll 1
         for (int r = 0; r < TR_LEVELS; ++r) {
-            u64 x[8];
+            u64 x[E];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = gadget_digit<F, GT>(u[k], r);
-            ntt_forward_regs<F>(x, (r & 1) ? wb : wa, tb.tw2, t, 0);
+            for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, GT>(u[k], r);
+            ntt_forward<AR, GEO, LdGlobal>(x, e0, tb.tw2, t, 0);
             const u64* ka = key + (size_t)r * 2 * N; const u64* kb = ka + N;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int idx = PassGeom<F, 3>::idx(t, k);
+            for (int k = 0; k < E; ++k) {
+                const int idx = out_idx<GEO>(t, k);
                 F::mac(ma[k], x[k], __ldg(ka + idx));
                 F::mac(mb[k], x[k], __ldg(kb + idx));
             }
         }
-        u64 ya[8], yb[8];
+        u64 ya[E], yb[E];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { ya[k] = F::redc(ma[k]); yb[k] = F::redc(mb[k]); }
-        __syncthreads();
-        ntt_inverse_regs2<F>(ya, yb, wa, wb, tb.itw2, t, 0);
+        for (int k = 0; k < E; ++k) { ya[k] = F::redc(ma[k]); yb[k] = F::redc(mb[k]); }
+        ntt_inverse2<AR, GEO, LdGlobal>(ya, yb, e0, e1, tb.itw2, t, 0);
         // b' = b + ks.b + sigma_d(b): read the permuted b before anyone overwrites it
-        u64 sb[8];
+        u64 sb[E];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { i64 v = automorphed(acc + N, t + NT * k, dinv); sb[k] = (u64)(v < 0 ? v + (i64)F::Q : v); }
+        for (int k = 0; k < E; ++k) { i64 v = automorphed(acc + N, t + GEO::NT * k, dinv); sb[k] = (u64)(v < 0 ? v + (i64)F::Q : v); }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int pos = t + NT * k;
+        for (int k = 0; k < E; ++k) {
+            const int pos = t + GEO::NT * k;
             acc[pos] = F::add_canon(acc[pos], ya[k]);
             acc[N + pos] = F::add_canon(F::csub(acc[N + pos] + sb[k], F::Q), yb[k]);
         }
         __syncthreads();
     }
     // to_ntt_rlwe (detector.rs:638): forward NTT of a and b, canonical output
-#pragma unroll 1
-    for (int p = 0; p < 2; ++p) {
-        u64 x[8];
+    u64 x[E], y[E];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = acc[p * N + t + NT * k];
-        ntt_forward_regs<F>(x, p ? wb : wa, tb.tw2, t, 0);
+    for (int k = 0; k < E; ++k) { x[k] = acc[t + GEO::NT * k]; y[k] = acc[N + t + GEO::NT * k]; }
+    ntt_forward2<AR, GEO, LdGlobal>(x, y, e0, e1, tb.tw2, t, 0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[p * N + PassGeom<F, 3>::idx(t, k)] = F::canon_lazy(x[k]);
-    }
+    for (int k = 0; k < E; ++k) { g[out_idx<GEO>(t, k)] = F::canon_lazy(x[k]); g[N + out_idx<GEO>(t, k)] = F::canon_lazy(y[k]); }
 }
 
 // ---- K5 / K6: digest packing ------------------------------------------------------------------------------------------
@@ -411,8 +432,8 @@ struct PackIndexArgs {            // detector.rs:223-339 + RetrievalParams
 struct PackPayloadArgs {          // detector.rs:341-453
     const unsigned short* payloads; const unsigned short* weights; size_t weight_stride; u32 cmb_per_cipher;
 };
-constexpr int PACK_THREADS = 256, PACK_CHUNK = 128;
-constexpr size_t PACK_SMEM = (size_t)2 * F2::N * sizeof(u64);
+constexpr int PACK_THREADS = GeoL2::NT, PACK_CHUNK = 128;
+constexpr size_t PACK_SMEM = (size_t)2 * GeoL2::BUF * 8;
 
 __device__ __forceinline__ u64 mix64(u64 z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
@@ -429,24 +450,24 @@ template <bool INDICES>
 __global__ void __launch_bounds__(PACK_THREADS, 2)
 pack_kernel(const u64* __restrict__ pv, size_t count, u64 index0, PackIndexArgs ia, PackPayloadArgs pa,
             u64* __restrict__ partial /*[n_cipher][n_chunks][2][N]*/, Tables tb) {
+    typedef F2 F; typedef F::Acc Acc; typedef GeoL2 GEO; typedef ArInt<F2> AR;
+    constexpr int N = F::N, E = GEO::E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64* wa = reinterpret_cast<u64*>(smem_raw); u64* wb = wa + F2::N;
-    typedef F2 F; typedef F::Acc Acc;
-    constexpr int N = F::N, NT = N / 8;
+    u64* bufs = reinterpret_cast<u64*>(smem_raw);
+    ExBuf<u64> eb{bufs, bufs + GEO::BUF};
     const int t = threadIdx.x, cipher = blockIdx.x, chunk = blockIdx.y;
     const size_t m_begin = (size_t)chunk * PACK_CHUNK, m_end = min(count, m_begin + PACK_CHUNK);
-    Acc ma[8], mb[8];
+    Acc ma[E], mb[E];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { ma[k] = Acc(); mb[k] = Acc(); }
-    int parity = 0;
+    for (int k = 0; k < E; ++k) { ma[k] = Acc(); mb[k] = Acc(); }
 #pragma unroll 1
-    for (size_t m = m_begin; m < m_end; ++m, parity ^= 1) {
+    for (size_t m = m_begin; m < m_end; ++m) {
         const u64 gi = index0 + m;
-        u64 x[8];
+        u64 x[E];
         if (INDICES) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const u32 pos = t + NT * k;
+            for (int k = 0; k < E; ++k) {
+                const u32 pos = t + GEO::NT * k;
                 const u32 seg = pos / ia.slots_per_segment, off = pos % ia.slots_per_segment;
                 u64 v = 0;
                 if (seg < ia.segment_per_cipher) {
@@ -466,8 +487,8 @@ pack_kernel(const u64* __restrict__ pv, size_t count, u64 index0, PackIndexArgs 
         } else {
             const unsigned short* pl = pa.payloads + m * PAYLOAD_LEN;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const u32 pos = t + NT * k;
+            for (int k = 0; k < E; ++k) {
+                const u32 pos = t + GEO::NT * k;
                 const u32 j = pos / PAYLOAD_LEN, kk = pos % PAYLOAD_LEN;
                 u64 v = 0;
                 if (j < pa.cmb_per_cipher) {
@@ -477,19 +498,19 @@ pack_kernel(const u64* __restrict__ pv, size_t count, u64 index0, PackIndexArgs 
                 x[k] = v;
             }
         }
-        ntt_forward_regs<F>(x, parity ? wb : wa, tb.tw2, t, 0);
+        ntt_forward<AR, GEO, LdGlobal>(x, eb, tb.tw2, t, 0);
         const u64* pa_ = pv + m * 2 * N; const u64* pb_ = pa_ + N;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int idx = PassGeom<F, 3>::idx(t, k);
+        for (int k = 0; k < E; ++k) {
+            const int idx = out_idx<GEO>(t, k);
             F::mac(ma[k], x[k], __ldg(pa_ + idx));
             F::mac(mb[k], x[k], __ldg(pb_ + idx));
         }
     }
     u64* o = partial + ((size_t)cipher * gridDim.y + chunk) * 2 * N;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int idx = PassGeom<F, 3>::idx(t, k);
+    for (int k = 0; k < E; ++k) {
+        const int idx = out_idx<GEO>(t, k);
         o[idx] = F::csub(F::mul_shoup(F::redc(ma[k]), tb.r2), F::Q);
         o[N + idx] = F::csub(F::mul_shoup(F::redc(mb[k]), tb.r2), F::Q);
     }
@@ -510,31 +531,43 @@ __global__ void digest_mod_kernel(u64* words, size_t n) {
 }
 
 // ---- standalone batched NTTs (key upload in coefficient form, tests, API completeness) -----------------------------
+template <class F> struct GeoOf;
+template <> struct GeoOf<F1> { typedef GeoL1 G; };
+template <> struct GeoOf<F2> { typedef GeoL2 G; };
+template <class F> __device__ __forceinline__ const typename F::TW* fwd_tw(const Tables& tb);
+template <> __device__ __forceinline__ const uint2* fwd_tw<F1>(const Tables& tb) { return tb.tw1; }
+template <> __device__ __forceinline__ const ulonglong2* fwd_tw<F2>(const Tables& tb) { return tb.tw2; }
+template <class F> __device__ __forceinline__ const typename F::TW* inv_tw(const Tables& tb);
+template <> __device__ __forceinline__ const uint2* inv_tw<F1>(const Tables& tb) { return tb.itw1; }
+template <> __device__ __forceinline__ const ulonglong2* inv_tw<F2>(const Tables& tb) { return tb.itw2; }
+
 template <class F, bool INVERSE>
-__global__ void __launch_bounds__(F::N / 8) ntt_kernel(typename F::T* data, Tables tb, typename F::TW n_inv) {
+__global__ void __launch_bounds__(256) ntt_kernel(typename F::T* data, Tables tb, typename F::TW n_inv) {
+    typedef typename F::T T; typedef typename GeoOf<F>::G GEO; typedef ArInt<F> AR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef typename F::T T;
-    T* w = reinterpret_cast<T*>(smem_raw);
-    constexpr int NT = F::N / 8;
+    T* bufs = reinterpret_cast<T*>(smem_raw);
+    ExBuf<T> eb{bufs, bufs + GEO::BUF};
     const int t = threadIdx.x;
     T* g = data + (size_t)blockIdx.x * F::N;
-    T x[8];
+    T x[GEO::E];
     if (!INVERSE) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = g[t + NT * k];
-        ntt_forward_regs<F>(x, w, fwd_tw<F>(tb), t, 0);
+        for (int k = 0; k < GEO::E; ++k) x[k] = g[t + GEO::NT * k];
+        ntt_forward<AR, GEO, LdGlobal>(x, eb, fwd_tw<F>(tb), t, 0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[PassGeom<F, 3>::idx(t, k)] = F::canon_lazy(x[k]);
+        for (int k = 0; k < GEO::E; ++k) g[out_idx<GEO>(t, k)] = F::canon_lazy(x[k]);
     } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = g[PassGeom<F, 3>::idx(t, k)];
-        ntt_inverse_regs<F>(x, w, inv_tw<F>(tb), t, 0);
+        for (int k = 0; k < GEO::E; ++k) x[k] = g[out_idx<GEO>(t, k)];
+        ntt_inverse<AR, GEO, LdGlobal>(x, eb, inv_tw<F>(tb), t, 0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[t + NT * k] = F::csub(F::mul_shoup(F::canon_lazy(x[k]), n_inv), F::Q);
+        for (int k = 0; k < GEO::E; ++k) g[t + GEO::NT * k] = F::csub(F::mul_shoup(F::canon_lazy(x[k]), n_inv), F::Q);
     }
 }
+template <class F> constexpr size_t ntt_kernel_smem() { return (size_t)2 * GeoOf<F>::G::BUF * sizeof(typename F::T); }
+template <class F> constexpr int ntt_kernel_threads() { return GeoOf<F>::G::NT; }
 
-// key pre-transform: word -> word * c mod q (c = R * N^-1, Shoup pair), optionally re-striding rows (KSK 671 -> 672)
+// key pre-transforms: word -> word * c mod q (c = R * N^-1, Shoup pair); KSK rows re-strided 671 -> 672
 template <class F>
 __global__ void scale_kernel(const typename F::T* __restrict__ in, typename F::T* __restrict__ out, size_t n, typename F::TW c) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -580,6 +613,29 @@ __global__ void __launch_bounds__(256) mulmod_peak_kernel(typename F::T* sink, t
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc += x[k];
     if (acc == (T)0x12345) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+// the same loop with the FP64 butterfly of the level-2 kernel (6-op exact mulmod + add/sub)
+__global__ void __launch_bounds__(256) mulmod_peak_f64_kernel(double* sink, double2 w, int iters) {
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (double)(threadIdx.x * 8 + k + 1);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double u = x[k], v = D2::mulmod(x[k + 4], w.x, w.y);
+            x[k] = __dadd_rn(u, v); x[k + 4] = __dadd_rn(u, -v);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const double u = D2::renorm(x[k]), v = D2::mulmod(x[k + 1], w.x, w.y);
+            x[k] = __dadd_rn(u, v); x[k + 1] = __dadd_rn(u, -v);
+        }
+    }
+    double acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += x[k];
+    if (acc == 12345.0) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
 }  // namespace omr

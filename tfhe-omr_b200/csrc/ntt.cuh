@@ -1,215 +1,263 @@
-// ntt.cuh — negacyclic NTT / INTT over Z_q[X]/(X^N+1), cooperative over a group of NT = N/8 threads.
-// Replaces [UPSTREAM] Primus-fhe algebra::ntt (concrete-ntt plans) as used by blind_rotate / trace / transform_slice
-// (detector.rs:325,435,555,623,638).  Same transform as the oracle: Cooley-Tukey forward, natural order
-// in, bit-reversed order out; Gentleman-Sande inverse (unscaled here: N^-1 is folded into the key material).
+// ntt.cuh — negacyclic NTT / INTT over Z_q[X]/(X^N+1), cooperative over a group of NT threads, E coefficients per
+// thread held in registers.  Replaces [UPSTREAM] Primus-fhe algebra::ntt (concrete-ntt plans) as used by blind_rotate /
+// trace / transform_slice (detector.rs:325,435,555,623,638).  Same transform as the oracle: Cooley-Tukey
+// forward, natural order in, bit-reversed order out; Gentleman-Sande inverse (unscaled: N^-1 lives in the key material).
 //
-// Each thread owns 8 coefficients in registers.  The log2(N) stages are cut into passes of 3 (last pass: 1 or 2)
-// stages; inside a pass all butterflies are register-to-register, between passes the group exchanges through a
-// swizzled shared-memory buffer (one barrier per exchange).  Forward butterflies are Harvey/Shoup and never reduce:
-// q1 < 2^27 leaves 21q < 2^32 after 10 stages, q2 < 2^50 leaves 23q << 2^64 after 11.
+// The log2(N) stages are cut into passes (L1: 4+4+2 with 16 coefficients/thread, L2: 3+3+3+2 with 8).  Inside a pass
+// all butterflies are register-to-register; between passes the group exchanges through shared memory.  Each exchange
+// has its own padded layout  phys(i) = i + A*(i >> S)  chosen (scripts/layout_check.py) so that both the writer and the
+// reader are bank-conflict free AND every address is (per-thread base) + (compile-time constant): the inner loops carry
+// no index arithmetic, and the last pass moves 16-byte vectors.  Exchanges alternate between two buffers so one barrier
+// per exchange suffices.
 #pragma once
 #include "field.cuh"
 
 namespace omr {
 
-// ---- bank-conflict-free swizzles of the exchange buffer (derived by search; checked in tests/test_layout.py) ----
-// u32, N=1024, 32 lanes x 4 B:  b0^=i5, b1^=i5, b2^=i6, b3^=i7, b4^=i7
-__device__ __forceinline__ int swz(F1, int x) { return x ^ ((((x >> 5) & 1) * 3) | (((x >> 6) & 1) * 4) | (((x >> 7) & 1) * 24)); }
-// u64, N=2048, half-warps of 16 lanes x 8 B:  b0^=i4, b1^=i5, b2^=i5, b3^=i6
-__device__ __forceinline__ int swz(F2, int x) { return x ^ (((x >> 4) & 1) | (((x >> 5) & 1) * 6) | (((x >> 6) & 1) * 8)); }
-
-template <class F> struct Plan {
-    static constexpr int N = F::N, LOGN = F::LOGN, NT = F::N / 8;
-    static constexpr int NPASS = 4;
-    static constexpr int LAST_NS = LOGN - 9;   // 1 (N=1024) or 2 (N=2048)
-    __host__ __device__ static constexpr int ns(int p) { return p < 3 ? 3 : LAST_NS; }
-    __host__ __device__ static constexpr int s0(int p) { return 3 * p; }
+template <int N_, int LOGN_, int NT_, int E_, int NP_, int NS0, int NS1, int NS2, int NS3, int A0, int S0_, int A1, int S1_, int A2, int S2_>
+struct GeoT {
+    static constexpr int N = N_, LOGN = LOGN_, NT = NT_, E = E_, NPASS = NP_;
+    __host__ __device__ static constexpr int ns(int p) { return p == 0 ? NS0 : p == 1 ? NS1 : p == 2 ? NS2 : NS3; }
+    __host__ __device__ static constexpr int s0(int p) { return p == 0 ? 0 : p == 1 ? NS0 : p == 2 ? NS0 + NS1 : NS0 + NS1 + NS2; }
+    __host__ __device__ static constexpr int pad_a(int x) { return x == 0 ? A0 : x == 1 ? A1 : A2; }
+    __host__ __device__ static constexpr int pad_s(int x) { return x == 0 ? S0_ : x == 1 ? S1_ : S2_; }
+    __host__ __device__ static constexpr int phys(int x, int i) { return pad_a(x) ? i + pad_a(x) * (i >> pad_s(x)) : i; }
+    __host__ __device__ static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+    // elements per exchange buffer (max over exchanges, rounded up to 4)
+    static constexpr int BUF = (cmax(cmax(phys(0, N - 1), phys(1, N - 1)), NP_ > 3 ? phys(2, N - 1) : 0) + 1 + 3) & ~3;
 };
+typedef GeoT<1024, 10, 64, 16, 3, 4, 4, 2, 0, 4, 6, 4, 6, 0, 0> GeoL1;     // 4-byte elements
+typedef GeoT<2048, 11, 256, 8, 4, 3, 3, 3, 2, 0, 0, 4, 5, 2, 4> GeoL2;     // 8-byte elements
 
-// Index of element k (0..7) of thread t in pass P:  group g = k / EP, kk = k % EP, vt = t + NT*g,
+// Pass P of geometry GEO: element k (0..E-1) of thread t:  group g = k / EP, kk = k % EP, vt = t + NT*g,
 //   blk = N >> S0, stride = blk / EP, j = vt / stride, i = vt % stride, idx = j*blk + i + kk*stride.
-template <class F, int P> struct PassGeom {
-    typedef Plan<F> PL;
-    static constexpr int S0 = PL::s0(P), NS = PL::ns(P), EP = 1 << NS, G = 8 / EP;
-    static constexpr int BLK = F::N >> S0, STRIDE = BLK / EP;
-    static __device__ __forceinline__ int block_of(int t, int g) { return (t + PL::NT * g) / STRIDE; }
-    static __device__ __forceinline__ int idx(int t, int k) {
-        const int g = k / EP, kk = k % EP, vt = t + PL::NT * g;
-        const int j = vt / STRIDE, i = vt % STRIDE;
-        return j * BLK + i + kk * STRIDE;
+template <class GEO, int P> struct Pass {
+    static constexpr int S0 = GEO::s0(P), NS = GEO::ns(P), EP = 1 << NS, G = GEO::E / EP;
+    static constexpr int BLK = GEO::N >> S0, STRIDE = BLK / EP;
+    __host__ __device__ static constexpr int idx(int t, int k) {
+        return ((t + GEO::NT * (k / EP)) / STRIDE) * BLK + ((t + GEO::NT * (k / EP)) % STRIDE) + (k % EP) * STRIDE;
     }
+    static __device__ __forceinline__ int block_of(int t, int g) { return (t + GEO::NT * g) / STRIDE; }
+    // physical offset of element k relative to element 0 in exchange X (thread independent, checked by layout_check.py)
+    template <int X> __host__ __device__ static constexpr int off(int k) { return GEO::phys(X, idx(0, k)) - GEO::phys(X, idx(0, 0)); }
+    template <int X> static __device__ __forceinline__ int base(int t) { return GEO::phys(X, idx(t, 0)); }
 };
 
-template <class F, int P> __device__ __forceinline__ void pass_load(typename F::T (&x)[8], const typename F::T* w, int t) {
+template <class T, int VE> struct VecOf;
+template <> struct VecOf<u32, 4> { typedef uint4 V; };
+template <> struct VecOf<u64, 2> { typedef ulonglong2 V; };
+template <> struct VecOf<double, 2> { typedef double2 V; };
+
+// store / load the E registers of pass P to / from exchange X
+template <class GEO, int P, int X, class T> __device__ __forceinline__ void ex_store(const T (&x)[GEO::E], T* buf, int t) {
+    typedef Pass<GEO, P> PS;
+    T* b = buf + PS::template base<X>(t);
+    if constexpr (PS::STRIDE == 1 && PS::EP * sizeof(T) >= 16) {
+        constexpr int VE = 16 / sizeof(T);
+        typedef typename VecOf<T, VE>::V V;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = w[swz(F(), PassGeom<F, P>::idx(t, k))];
+        for (int k = 0; k < GEO::E; k += VE) {
+            V v;
+            T* pv = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) pv[e] = x[k + e];
+            *reinterpret_cast<V*>(b + PS::template off<X>(k)) = v;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < GEO::E; ++k) b[PS::template off<X>(k)] = x[k];
+    }
 }
-template <class F, int P> __device__ __forceinline__ void pass_store(const typename F::T (&x)[8], typename F::T* w, int t) {
+template <class GEO, int P, int X, class T> __device__ __forceinline__ void ex_load(T (&x)[GEO::E], const T* buf, int t) {
+    typedef Pass<GEO, P> PS;
+    const T* b = buf + PS::template base<X>(t);
+    if constexpr (PS::STRIDE == 1 && PS::EP * sizeof(T) >= 16) {
+        constexpr int VE = 16 / sizeof(T);
+        typedef typename VecOf<T, VE>::V V;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) w[swz(F(), PassGeom<F, P>::idx(t, k))] = x[k];
+        for (int k = 0; k < GEO::E; k += VE) {
+            const V v = *reinterpret_cast<const V*>(b + PS::template off<X>(k));
+            const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) x[k + e] = pv[e];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < GEO::E; ++k) x[k] = b[PS::template off<X>(k)];
+    }
 }
 
-// forward butterflies of pass P on registers
-template <class F, int P> __device__ __forceinline__ void fwd_pass(typename F::T (&x)[8], const typename F::TW* __restrict__ tw, int t) {
-    typedef PassGeom<F, P> GEO; typedef typename F::T T;
+// ---- arithmetic policies ---------------------------------------------------------------------------------------------
+// integer Harvey/Shoup butterflies; forward never reduces (q1: 21q < 2^32 after 10 stages, q2: 23q << 2^64 after 11)
+template <class F> struct ArInt {
+    typedef typename F::T T; typedef typename F::TW TW;
+    static constexpr int LOGN = F::LOGN;
+    template <int S0, int E> static __device__ __forceinline__ void pre_fwd(T (&)[E]) {}
+    template <int STAGE> static __device__ __forceinline__ void fwd(T& a, T& b, TW w) {
+        const T u = a, v = F::mul_shoup(b, w);
+        a = u + v; b = u - v + 2 * F::Q;
+    }
+    template <int STAGE> static __device__ __forceinline__ void inv(T& a, T& b, TW w) {
+        constexpr int done = LOGN - 1 - STAGE;                 // Gentleman-Sande stages completed before this one
+        const T u = a, v = b;
+        a = F::inv_add(u, v, done); b = F::mul_shoup(F::inv_sub(u, v, done), w);
+    }
+};
+// level 2 on the FP64 pipe (D2 in field.cuh).  Lazy ranges of the forward transform (|mulmod| < 0.76q, growth 0.76q per
+// stage): stages 0-5 from |x| <= 65 reach 4.6q (< 8q exact; mulmod inputs <= 3.8q), renormalise at the start of the pass
+// that begins at stage 6, stages 6-9 reach 3.6q, and the last stage renormalises its pass-through operand, so outputs
+// are <= 1.3q.  Inverse: inputs < 0.76q; sums are renormalised, differences (< 1.6q) go through mulmod.
+struct ArD2 {
+    typedef double T; typedef double2 TW;
+    static constexpr int LOGN = 11;
+    template <int S0, int E> static __device__ __forceinline__ void pre_fwd(T (&x)[E]) {
+        if (S0 == 6) {
 #pragma unroll
-    for (int g = 0; g < GEO::G; ++g) {
-        const int j = GEO::block_of(t, g);
+            for (int k = 0; k < E; ++k) x[k] = D2::renorm(x[k]);
+        }
+    }
+    template <int STAGE> static __device__ __forceinline__ void fwd(T& a, T& b, TW w) {
+        const T u = (STAGE == LOGN - 1) ? D2::renorm(a) : a;
+        const T v = D2::mulmod(b, w.x, w.y);
+        a = __dadd_rn(u, v); b = __dadd_rn(u, -v);
+    }
+    template <int STAGE> static __device__ __forceinline__ void inv(T& a, T& b, TW w) {
+        const T u = a, v = b;
+        a = D2::renorm(__dadd_rn(u, v)); b = D2::mulmod(__dadd_rn(u, -v), w.x, w.y);
+    }
+};
+struct LdGlobal { template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return __ldg(p); } };
+struct LdShared { template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
+
+template <class AR, class GEO, int P, class LD>
+__device__ __forceinline__ void fwd_pass(typename AR::T (&x)[GEO::E], const typename AR::TW* __restrict__ tw, int t) {
+    typedef Pass<GEO, P> PS;
+    AR::template pre_fwd<PS::S0, GEO::E>(x);
 #pragma unroll
-        for (int l = 0; l < GEO::NS; ++l) {
-            const int half = GEO::EP >> (l + 1);
+    for (int g = 0; g < PS::G; ++g) {
+        const int j = PS::block_of(t, g);
+#pragma unroll
+        for (int l = 0; l < PS::NS; ++l) {
+            const int half = PS::EP >> (l + 1);
 #pragma unroll
             for (int sb = 0; sb < (1 << l); ++sb) {
-                const typename F::TW w = __ldg(&tw[(1 << (GEO::S0 + l)) + (j << l) + sb]);
+                const typename AR::TW w = LD::ld(&tw[(1 << (PS::S0 + l)) + (j << l) + sb]);
 #pragma unroll
                 for (int h = 0; h < half; ++h) {
-                    const int lo = g * GEO::EP + sb * 2 * half + h, hi = lo + half;
-                    T u = x[lo], v = F::mul_shoup(x[hi], w);
-                    x[lo] = u + v; x[hi] = u - v + 2 * F::Q;
+                    const int lo = g * PS::EP + sb * 2 * half + h, hi = lo + half;
+                    // STAGE must be a compile-time constant: dispatch on l (NS <= 4)
+                    if (l == 0) AR::template fwd<PS::S0 + 0>(x[lo], x[hi], w);
+                    else if (l == 1) AR::template fwd<PS::S0 + 1>(x[lo], x[hi], w);
+                    else if (l == 2) AR::template fwd<PS::S0 + 2>(x[lo], x[hi], w);
+                    else AR::template fwd<PS::S0 + 3>(x[lo], x[hi], w);
+                }
+            }
+        }
+    }
+}
+template <class AR, class GEO, int P, class LD>
+__device__ __forceinline__ void inv_pass(typename AR::T (&x)[GEO::E], const typename AR::TW* __restrict__ itw, int t) {
+    typedef Pass<GEO, P> PS;
+#pragma unroll
+    for (int g = 0; g < PS::G; ++g) {
+        const int j = PS::block_of(t, g);
+#pragma unroll
+        for (int l = PS::NS - 1; l >= 0; --l) {
+            const int half = PS::EP >> (l + 1);
+#pragma unroll
+            for (int sb = 0; sb < (1 << l); ++sb) {
+                const typename AR::TW w = LD::ld(&itw[(1 << (PS::S0 + l)) + (j << l) + sb]);
+#pragma unroll
+                for (int h = 0; h < half; ++h) {
+                    const int lo = g * PS::EP + sb * 2 * half + h, hi = lo + half;
+                    if (l == 0) AR::template inv<PS::S0 + 0>(x[lo], x[hi], w);
+                    else if (l == 1) AR::template inv<PS::S0 + 1>(x[lo], x[hi], w);
+                    else if (l == 2) AR::template inv<PS::S0 + 2>(x[lo], x[hi], w);
+                    else AR::template inv<PS::S0 + 3>(x[lo], x[hi], w);
                 }
             }
         }
     }
 }
 
-// inverse (Gentleman-Sande) butterflies of pass P on registers; stages run in reverse order
-template <class F, int P> __device__ __forceinline__ void inv_pass(typename F::T (&x)[8], const typename F::TW* __restrict__ itw, int t) {
-    typedef PassGeom<F, P> GEO; typedef typename F::T T;
-#pragma unroll
-    for (int g = 0; g < GEO::G; ++g) {
-        const int j = GEO::block_of(t, g);
-#pragma unroll
-        for (int l = GEO::NS - 1; l >= 0; --l) {
-            const int half = GEO::EP >> (l + 1);
-            const int done = F::LOGN - 1 - (GEO::S0 + l);     // GS stages completed before this one
-#pragma unroll
-            for (int sb = 0; sb < (1 << l); ++sb) {
-                const typename F::TW w = __ldg(&itw[(1 << (GEO::S0 + l)) + (j << l) + sb]);
-#pragma unroll
-                for (int h = 0; h < half; ++h) {
-                    const int lo = g * GEO::EP + sb * 2 * half + h, hi = lo + half;
-                    T u = x[lo], v = x[hi];
-                    x[lo] = F::inv_add(u, v, done);
-                    x[hi] = F::mul_shoup(F::inv_sub(u, v, done), w);
-                }
-            }
-        }
-    }
-}
-
-// group barrier: id 0 = whole CTA (__syncthreads), otherwise a named barrier over `nthreads`
+// group barrier: id 0 = whole CTA (__syncthreads), otherwise a named barrier over NTHREADS
 template <int NTHREADS> __device__ __forceinline__ void group_sync(int bar_id) {
     if (bar_id == 0) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NTHREADS) : "memory");
 }
 
-// Forward NTT: x holds pass-0 elements on entry (idx = t + NT*k), pass-3 elements on exit (lazy, unreduced).
-// w is the exchange buffer (N elements).  3 barriers.
-template <class F> __device__ __forceinline__ void ntt_forward_regs(typename F::T (&x)[8], typename F::T* w,
-                                                                      const typename F::TW* __restrict__ tw, int t, int bar) {
-    constexpr int NT = Plan<F>::NT;
-    fwd_pass<F, 0>(x, tw, t); pass_store<F, 0>(x, w, t); group_sync<NT>(bar);
-    pass_load<F, 1>(x, w, t); fwd_pass<F, 1>(x, tw, t); pass_store<F, 1>(x, w, t); group_sync<NT>(bar);
-    pass_load<F, 2>(x, w, t); fwd_pass<F, 2>(x, tw, t); pass_store<F, 2>(x, w, t); group_sync<NT>(bar);
-    pass_load<F, 3>(x, w, t); fwd_pass<F, 3>(x, tw, t);
+// two exchange buffers used alternately by EVERY exchange of the group (forward, inverse, any polynomial): a write to
+// one buffer is always separated from the last read of it by the barrier of the exchange in between.
+template <class T> struct ExBuf {
+    T* a; T* b;
+    __device__ __forceinline__ T* next() { T* r = a; a = b; b = r; return r; }
+};
+
+// Forward NTT: x holds pass-0 elements (idx = t + NT*k) on entry, last-pass elements on exit (lazy, unreduced).
+template <class AR, class GEO, class LD>
+__device__ __forceinline__ void ntt_forward(typename AR::T (&x)[GEO::E], ExBuf<typename AR::T>& eb, const typename AR::TW* __restrict__ tw, int t, int bar) {
+    typedef typename AR::T T;
+    fwd_pass<AR, GEO, 0, LD>(x, tw, t);
+    { T* w = eb.next(); ex_store<GEO, 0, 0>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 1, 0>(x, w, t); }
+    fwd_pass<AR, GEO, 1, LD>(x, tw, t);
+    { T* w = eb.next(); ex_store<GEO, 1, 1>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 2, 1>(x, w, t); }
+    fwd_pass<AR, GEO, 2, LD>(x, tw, t);
+    if constexpr (GEO::NPASS == 4) {
+        { T* w = eb.next(); ex_store<GEO, 2, 2>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 3, 2>(x, w, t); }
+        fwd_pass<AR, GEO, 3, LD>(x, tw, t);
+    }
 }
-// Inverse NTT (unscaled): x holds pass-3 elements (< 2q) on entry, pass-0 elements on exit.  3 barriers.
-template <class F> __device__ __forceinline__ void ntt_inverse_regs(typename F::T (&x)[8], typename F::T* w,
-                                                                      const typename F::TW* __restrict__ itw, int t, int bar) {
-    constexpr int NT = Plan<F>::NT;
-    inv_pass<F, 3>(x, itw, t); pass_store<F, 3>(x, w, t); group_sync<NT>(bar);
-    pass_load<F, 2>(x, w, t); inv_pass<F, 2>(x, itw, t); pass_store<F, 2>(x, w, t); group_sync<NT>(bar);
-    pass_load<F, 1>(x, w, t); inv_pass<F, 1>(x, itw, t); pass_store<F, 1>(x, w, t); group_sync<NT>(bar);
-    pass_load<F, 0>(x, w, t); inv_pass<F, 0>(x, itw, t);
+// two forward NTTs sharing the barriers (second polynomial uses its own buffer pair)
+template <class AR, class GEO, class LD>
+__device__ __forceinline__ void ntt_forward2(typename AR::T (&x)[GEO::E], typename AR::T (&y)[GEO::E], ExBuf<typename AR::T>& ex, ExBuf<typename AR::T>& ey,
+                                             const typename AR::TW* __restrict__ tw, int t, int bar) {
+    typedef typename AR::T T;
+    fwd_pass<AR, GEO, 0, LD>(x, tw, t); fwd_pass<AR, GEO, 0, LD>(y, tw, t);
+    { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 0, 0>(x, w, t); ex_store<GEO, 0, 0>(y, v, t); group_sync<GEO::NT>(bar);
+      ex_load<GEO, 1, 0>(x, w, t); ex_load<GEO, 1, 0>(y, v, t); }
+    fwd_pass<AR, GEO, 1, LD>(x, tw, t); fwd_pass<AR, GEO, 1, LD>(y, tw, t);
+    { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 1, 1>(x, w, t); ex_store<GEO, 1, 1>(y, v, t); group_sync<GEO::NT>(bar);
+      ex_load<GEO, 2, 1>(x, w, t); ex_load<GEO, 2, 1>(y, v, t); }
+    fwd_pass<AR, GEO, 2, LD>(x, tw, t); fwd_pass<AR, GEO, 2, LD>(y, tw, t);
+    if constexpr (GEO::NPASS == 4) {
+        { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 2, 2>(x, w, t); ex_store<GEO, 2, 2>(y, v, t); group_sync<GEO::NT>(bar);
+          ex_load<GEO, 3, 2>(x, w, t); ex_load<GEO, 3, 2>(y, v, t); }
+        fwd_pass<AR, GEO, 3, LD>(x, tw, t); fwd_pass<AR, GEO, 3, LD>(y, tw, t);
+    }
 }
-// two inverse NTTs sharing the barriers (buffers wa, wb)
-template <class F> __device__ __forceinline__ void ntt_inverse_regs2(typename F::T (&xa)[8], typename F::T (&xb)[8], typename F::T* wa,
-                                                                       typename F::T* wb, const typename F::TW* __restrict__ itw, int t, int bar) {
-    constexpr int NT = Plan<F>::NT;
-    inv_pass<F, 3>(xa, itw, t); inv_pass<F, 3>(xb, itw, t); pass_store<F, 3>(xa, wa, t); pass_store<F, 3>(xb, wb, t); group_sync<NT>(bar);
-    pass_load<F, 2>(xa, wa, t); pass_load<F, 2>(xb, wb, t); inv_pass<F, 2>(xa, itw, t); inv_pass<F, 2>(xb, itw, t);
-    pass_store<F, 2>(xa, wa, t); pass_store<F, 2>(xb, wb, t); group_sync<NT>(bar);
-    pass_load<F, 1>(xa, wa, t); pass_load<F, 1>(xb, wb, t); inv_pass<F, 1>(xa, itw, t); inv_pass<F, 1>(xb, itw, t);
-    pass_store<F, 1>(xa, wa, t); pass_store<F, 1>(xb, wb, t); group_sync<NT>(bar);
-    pass_load<F, 0>(xa, wa, t); pass_load<F, 0>(xb, wb, t); inv_pass<F, 0>(xa, itw, t); inv_pass<F, 0>(xb, itw, t);
+// Inverse NTT (unscaled): x holds last-pass elements on entry, pass-0 elements on exit.
+template <class AR, class GEO, class LD>
+__device__ __forceinline__ void ntt_inverse(typename AR::T (&x)[GEO::E], ExBuf<typename AR::T>& eb, const typename AR::TW* __restrict__ itw, int t, int bar) {
+    typedef typename AR::T T;
+    if constexpr (GEO::NPASS == 4) {
+        inv_pass<AR, GEO, 3, LD>(x, itw, t);
+        { T* w = eb.next(); ex_store<GEO, 3, 2>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 2, 2>(x, w, t); }
+    }
+    inv_pass<AR, GEO, 2, LD>(x, itw, t);
+    { T* w = eb.next(); ex_store<GEO, 2, 1>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 1, 1>(x, w, t); }
+    inv_pass<AR, GEO, 1, LD>(x, itw, t);
+    { T* w = eb.next(); ex_store<GEO, 1, 0>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 0, 0>(x, w, t); }
+    inv_pass<AR, GEO, 0, LD>(x, itw, t);
+}
+template <class AR, class GEO, class LD>
+__device__ __forceinline__ void ntt_inverse2(typename AR::T (&x)[GEO::E], typename AR::T (&y)[GEO::E], ExBuf<typename AR::T>& ex, ExBuf<typename AR::T>& ey,
+                                             const typename AR::TW* __restrict__ itw, int t, int bar) {
+    typedef typename AR::T T;
+    if constexpr (GEO::NPASS == 4) {
+        inv_pass<AR, GEO, 3, LD>(x, itw, t); inv_pass<AR, GEO, 3, LD>(y, itw, t);
+        { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 3, 2>(x, w, t); ex_store<GEO, 3, 2>(y, v, t); group_sync<GEO::NT>(bar);
+          ex_load<GEO, 2, 2>(x, w, t); ex_load<GEO, 2, 2>(y, v, t); }
+    }
+    inv_pass<AR, GEO, 2, LD>(x, itw, t); inv_pass<AR, GEO, 2, LD>(y, itw, t);
+    { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 2, 1>(x, w, t); ex_store<GEO, 2, 1>(y, v, t); group_sync<GEO::NT>(bar);
+      ex_load<GEO, 1, 1>(x, w, t); ex_load<GEO, 1, 1>(y, v, t); }
+    inv_pass<AR, GEO, 1, LD>(x, itw, t); inv_pass<AR, GEO, 1, LD>(y, itw, t);
+    { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 1, 0>(x, w, t); ex_store<GEO, 1, 0>(y, v, t); group_sync<GEO::NT>(bar);
+      ex_load<GEO, 0, 0>(x, w, t); ex_load<GEO, 0, 0>(y, v, t); }
+    inv_pass<AR, GEO, 0, LD>(x, itw, t); inv_pass<AR, GEO, 0, LD>(y, itw, t);
 }
 
-// ---- FP64 variants for level 2 (same pass geometry / swizzle as F2; elements are integer-valued doubles) ------------
-// Lazy-range schedule of the forward transform (T = mulmod output, |T| < 0.76q; growth 0.76q per stage):
-//   stages 0-5 from |x| <= 65 reach 4.56q (< 8q exact; mulmod inputs <= 3.8q), renormalise at the start of pass 2,
-//   stages 6-9 reach 3.54q, and the last stage renormalises its pass-through operand so outputs are <= 1.26q.
-template <int P> __device__ __forceinline__ void pass_load_d(double (&x)[8], const double* w, int t) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = w[swz(F2(), PassGeom<F2, P>::idx(t, k))];
-}
-template <int P> __device__ __forceinline__ void pass_store_d(const double (&x)[8], double* w, int t) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w[swz(F2(), PassGeom<F2, P>::idx(t, k))] = x[k];
-}
-template <int P> __device__ __forceinline__ void fwd_pass_d(double (&x)[8], const double2* __restrict__ tw, int t) {
-    typedef PassGeom<F2, P> GEO;
-    if (P == 2) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = D2::renorm(x[k]);
-    }
-#pragma unroll
-    for (int g = 0; g < GEO::G; ++g) {
-        const int j = GEO::block_of(t, g);
-#pragma unroll
-        for (int l = 0; l < GEO::NS; ++l) {
-            const int half = GEO::EP >> (l + 1);
-            const bool last = (GEO::S0 + l == F2::LOGN - 1);
-#pragma unroll
-            for (int sb = 0; sb < (1 << l); ++sb) {
-                const double2 w = __ldg(&tw[(1 << (GEO::S0 + l)) + (j << l) + sb]);
-#pragma unroll
-                for (int h = 0; h < half; ++h) {
-                    const int lo = g * GEO::EP + sb * 2 * half + h, hi = lo + half;
-                    const double u = last ? D2::renorm(x[lo]) : x[lo];
-                    const double v = D2::mulmod(x[hi], w.x, w.y);
-                    x[lo] = __dadd_rn(u, v); x[hi] = __dadd_rn(u, -v);
-                }
-            }
-        }
-    }
-}
-// inverse (Gentleman-Sande): inputs |x| < 0.76q; sums are renormalised, differences (< 1.52q) go through mulmod
-template <int P> __device__ __forceinline__ void inv_pass_d(double (&x)[8], const double2* __restrict__ itw, int t) {
-    typedef PassGeom<F2, P> GEO;
-#pragma unroll
-    for (int g = 0; g < GEO::G; ++g) {
-        const int j = GEO::block_of(t, g);
-#pragma unroll
-        for (int l = GEO::NS - 1; l >= 0; --l) {
-            const int half = GEO::EP >> (l + 1);
-#pragma unroll
-            for (int sb = 0; sb < (1 << l); ++sb) {
-                const double2 w = __ldg(&itw[(1 << (GEO::S0 + l)) + (j << l) + sb]);
-#pragma unroll
-                for (int h = 0; h < half; ++h) {
-                    const int lo = g * GEO::EP + sb * 2 * half + h, hi = lo + half;
-                    const double u = x[lo], v = x[hi];
-                    x[lo] = D2::renorm(__dadd_rn(u, v));
-                    x[hi] = D2::mulmod(__dadd_rn(u, -v), w.x, w.y);
-                }
-            }
-        }
-    }
-}
-__device__ __forceinline__ void ntt_forward_regs_d(double (&x)[8], double* w, const double2* __restrict__ tw, int t) {
-    fwd_pass_d<0>(x, tw, t); pass_store_d<0>(x, w, t); __syncthreads();
-    pass_load_d<1>(x, w, t); fwd_pass_d<1>(x, tw, t); pass_store_d<1>(x, w, t); __syncthreads();
-    pass_load_d<2>(x, w, t); fwd_pass_d<2>(x, tw, t); pass_store_d<2>(x, w, t); __syncthreads();
-    pass_load_d<3>(x, w, t); fwd_pass_d<3>(x, tw, t);
-}
-__device__ __forceinline__ void ntt_inverse_regs2_d(double (&xa)[8], double (&xb)[8], double* wa, double* wb,
-                                                    const double2* __restrict__ itw, int t) {
-    inv_pass_d<3>(xa, itw, t); inv_pass_d<3>(xb, itw, t); pass_store_d<3>(xa, wa, t); pass_store_d<3>(xb, wb, t); __syncthreads();
-    pass_load_d<2>(xa, wa, t); pass_load_d<2>(xb, wb, t); inv_pass_d<2>(xa, itw, t); inv_pass_d<2>(xb, itw, t);
-    pass_store_d<2>(xa, wa, t); pass_store_d<2>(xb, wb, t); __syncthreads();
-    pass_load_d<1>(xa, wa, t); pass_load_d<1>(xb, wb, t); inv_pass_d<1>(xa, itw, t); inv_pass_d<1>(xb, itw, t);
-    pass_store_d<1>(xa, wa, t); pass_store_d<1>(xb, wb, t); __syncthreads();
-    pass_load_d<0>(xa, wa, t); pass_load_d<0>(xb, wb, t); inv_pass_d<0>(xa, itw, t); inv_pass_d<0>(xb, itw, t);
-}
+// index of element k of thread t after the forward transform (= NTT-domain coefficient index, bit-reversed order)
+template <class GEO> __host__ __device__ constexpr int out_idx(int t, int k) { return Pass<GEO, GEO::NPASS - 1>::idx(t, k); }
 
 }  // namespace omr
