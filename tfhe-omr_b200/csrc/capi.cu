@@ -59,6 +59,7 @@ struct omr_ctx {
     size_t key_bytes = 0;
     // scratch for the batched pipeline, sized for `cap` messages
     size_t cap = 0; u32* s_rlwe1 = nullptr; u32* s_lwe2 = nullptr; unsigned short *s_ca = nullptr, *s_cb = nullptr;
+    size_t cap7 = 0; u32* s_rlwe7 = nullptr;      // per-(message, clue) accumulators of the L1 kernel
     // packing scratch
     u64* s_partial = nullptr; size_t partial_words = 0;
     u64* s_digest = nullptr; size_t digest_words = 0;
@@ -107,7 +108,15 @@ int ensure_pv(omr_ctx* ctx, size_t need) {
 // ---- launches -------------------------------------------------------------------------------------------------------
 int launch_l1(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* out, cudaStream_t s) {
     if (!B) return OMR_OK;
-    l1_blind_rotate_kernel<<<(unsigned)B, L1_THREADS, L1_SMEM, s>>>(ca, cb, ctx->bsk1, out, ctx->tb);
+    if (B > ctx->cap7) {
+        if (ctx->s_rlwe7) { CK(cudaStreamSynchronize(s)); cudaFree(ctx->s_rlwe7); ctx->s_rlwe7 = nullptr; ctx->cap7 = 0; }
+        CK(cudaMalloc((void**)&ctx->s_rlwe7, B * CLUE_COUNT * 2 * F1::N * sizeof(u32)));
+        ctx->cap7 = B;
+    }
+    const size_t n_clues = B * CLUE_COUNT;
+    l1_blind_rotate_kernel<<<(unsigned)((n_clues + L1_SLOTS - 1) / L1_SLOTS), L1_THREADS, L1_SMEM, s>>>(ca, cb, ctx->bsk1, ctx->s_rlwe7, (int)n_clues, ctx->tb);
+    ++ctx->launches; CK(cudaGetLastError());
+    sum7_kernel<<<(unsigned)((B * 2 * F1::N + 255) / 256), 256, 0, s>>>(ctx->s_rlwe7, out, B);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
@@ -311,7 +320,7 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
-                    ctx->s_rlwe1, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
+                    ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -117,43 +117,49 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, u32 bytes, 
                  : "memory");
 }
 
-// ---- K1: first-level blind rotations + sum -----------------------------------------------------------------------
-// One CTA per message: 7 groups of 64 threads (one per clue), 16 coefficients per thread, each group with its own
-// accumulator and exchange buffers (named barriers only inside the loop body).  Per CMux step the 64 KiB RGSW tile
-// BSK1[i] is staged ONCE into shared memory by a TMA bulk copy and reused by all 7 clues; the copy of tile i+1 is in
-// flight while the groups run their inverse transforms and the first forward transform of the next step.  Twiddles
-// live in shared memory.  clue extraction (CmLwe::extract_all, detector.rs:514) is index arithmetic on the fly.
+// ---- K1: first-level blind rotations ---------------------------------------------------------------------------------
+// A CTA runs 8 blind rotations at once — 8 consecutive (message, clue) pairs of the batch — one per group of 64 threads
+// (2 warps, 16 coefficients per thread): 16 warps = 4 per scheduler, and every blind rotation walks the same key
+// sequence BSK1[0..511], so per CMux step the 64 KiB RGSW tile is staged ONCE into shared memory by a TMA bulk copy and
+// reused by all 8 groups; the copy of tile i+1 is in flight while the groups run their inverse transforms and the first
+// forward transform of the next step.  Twiddles live in shared memory.  Clue extraction (CmLwe::extract_all,
+// detector.rs:514) is index arithmetic on the fly.  Output: one RLWE accumulator per (message, clue); sum7_kernel adds
+// the 7 accumulators of a message (add_element_wise, detector.rs:556).
 constexpr int L1_GROUP = GeoL1::NT;                        // 64
-constexpr int L1_THREADS = CLUE_COUNT * L1_GROUP;          // 448
+constexpr int L1_SLOTS = 8;
+constexpr int L1_THREADS = L1_SLOTS * L1_GROUP;            // 512
 constexpr int L1_TILE_WORDS = 2 * G1::LEVELS * 2 * F1::N;  // 16384 u32 = 64 KiB
 constexpr int L1_GROUP_WORDS = 2 * F1::N + 2 * GeoL1::BUF;
-constexpr size_t L1_SMEM = 128 /*align*/ + (size_t)L1_TILE_WORDS * 4 + 2 * F1::N * sizeof(uint2) + (size_t)CLUE_COUNT * L1_GROUP_WORDS * 4 +
-                           CLUE_N * sizeof(unsigned short) + 16;
+constexpr size_t L1_SMEM = (size_t)L1_TILE_WORDS * 4 + 2 * F1::N * sizeof(uint2) + (size_t)L1_SLOTS * L1_GROUP_WORDS * 4 +
+                           (size_t)L1_SLOTS * CLUE_N * sizeof(unsigned short) + 16;
 
 __global__ void __launch_bounds__(L1_THREADS, 1)
 l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned short* __restrict__ clue_b,
-                       const u32* __restrict__ bsk1, u32* __restrict__ out, Tables tb) {
+                       const u32* __restrict__ bsk1, u32* __restrict__ out /*[n_clues][2][N]*/, int n_clues, Tables tb) {
     typedef F1 F; typedef G1 G; typedef GeoL1 GEO; typedef ArInt<F1> AR;
     constexpr int N = F::N, E = GEO::E, L = G::LEVELS;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* sp = reinterpret_cast<unsigned char*>(((size_t)smem_dyn + 127) & ~(size_t)127);
-    u32* ktile = reinterpret_cast<u32*>(sp); sp += (size_t)L1_TILE_WORDS * 4;
-    uint2* s_tw = reinterpret_cast<uint2*>(sp); sp += N * sizeof(uint2);
-    uint2* s_itw = reinterpret_cast<uint2*>(sp); sp += N * sizeof(uint2);
-    u32* groups = reinterpret_cast<u32*>(sp); sp += (size_t)CLUE_COUNT * L1_GROUP_WORDS * 4;
-    unsigned short* ca = reinterpret_cast<unsigned short*>(sp); sp += CLUE_N * sizeof(unsigned short);
-    u64* mbar = reinterpret_cast<u64*>(((size_t)sp + 7) & ~(size_t)7);
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    u32* ktile = reinterpret_cast<u32*>(smem_dyn);
+    uint2* s_tw = reinterpret_cast<uint2*>(ktile + L1_TILE_WORDS);
+    uint2* s_itw = s_tw + N;
+    u32* groups = reinterpret_cast<u32*>(s_itw + N);
+    unsigned short* ca_all = reinterpret_cast<unsigned short*>(groups + (size_t)L1_SLOTS * L1_GROUP_WORDS);
+    u64* mbar = reinterpret_cast<u64*>(ca_all + L1_SLOTS * CLUE_N);
 
-    const int msg = blockIdx.x, c = threadIdx.x / L1_GROUP, t = threadIdx.x % L1_GROUP;
-    u32* acc = groups + (size_t)c * L1_GROUP_WORDS;       // [2][N]
+    const int slot = threadIdx.x / L1_GROUP, t = threadIdx.x % L1_GROUP;
+    const int cid_raw = blockIdx.x * L1_SLOTS + slot;
+    const int cid = cid_raw < n_clues ? cid_raw : n_clues - 1;        // tail groups redo the last clue (no store)
+    const int msg = cid / CLUE_COUNT, c = cid % CLUE_COUNT;
+    u32* acc = groups + (size_t)slot * L1_GROUP_WORDS;       // [2][N]
+    unsigned short* ca = ca_all + slot * CLUE_N;
     ExBuf<u32> eb{acc + 2 * N, acc + 2 * N + GEO::BUF};
     if (threadIdx.x == 0) mbar_init(mbar, 1);
     for (int i = threadIdx.x; i < N; i += L1_THREADS) { s_tw[i] = tb.tw1[i]; s_itw[i] = tb.itw1[i]; }
-    for (int i = threadIdx.x; i < CLUE_N; i += L1_THREADS) ca[i] = clue_a[(size_t)msg * CLUE_N + i];
+    for (int i = t; i < CLUE_N; i += L1_GROUP) ca[i] = clue_a[(size_t)msg * CLUE_N + i];
     init_acc<F, GEO>(acc, tb.lut1, clue_b[(size_t)msg * CLUE_COUNT + c], t);
     __syncthreads();
     if (threadIdx.x == 0) tma_load(ktile, bsk1, L1_TILE_WORDS * 4, mbar);
-    const int bar = 1 + c;
+    const int bar = 1 + slot;
 #pragma unroll 1
     for (int i = 0; i < CLUE_N; ++i) {
         // a^(c)_i = a_{c-i} (i <= c), -a_{512+c-i} (i > c)   SURVEY A.3.   a == 0 is not skipped: (X^0 - 1) acc = 0
@@ -187,7 +193,7 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
         u32 ya[E], yb[E];
 #pragma unroll
         for (int k = 0; k < E; ++k) { ya[k] = F::inv_prepare(F::redc(ma[k])); yb[k] = F::inv_prepare(F::redc(mb[k])); }
-        __syncthreads();                                                         // every clue is done with tile i
+        __syncthreads();                                                         // every group is done with tile i
         if (threadIdx.x == 0 && i + 1 < CLUE_N) tma_load(ktile, bsk1 + (size_t)(i + 1) * L1_TILE_WORDS, L1_TILE_WORDS * 4, mbar);
         ntt_inverse<AR, GEO, LdShared>(ya, eb, s_itw, t, bar);
         ntt_inverse<AR, GEO, LdShared>(yb, eb, s_itw, t, bar);
@@ -199,27 +205,34 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
         }
         group_sync<GEO::NT>(bar);
     }
-    __syncthreads();
-    // sum of the 7 accumulators (add_element_wise, detector.rs:556)
-    for (int e = threadIdx.x; e < 2 * N; e += L1_THREADS) {
-        u32 s = 0;
+    if (cid_raw < n_clues) {
+        u32* o = out + (size_t)cid * 2 * N;
 #pragma unroll
-        for (int cc = 0; cc < CLUE_COUNT; ++cc) s += groups[(size_t)cc * L1_GROUP_WORDS + e];    // 7q < 2^30
-        out[(size_t)msg * 2 * N + e] = s % Q1;
+        for (int k = 0; k < 2 * E; ++k) o[t + GEO::NT * k] = acc[t + GEO::NT * k];
     }
+}
+// sum of the 7 accumulators of each message (detector.rs:556)
+__global__ void sum7_kernel(const u32* __restrict__ in /*[B*7][2][N]*/, u32* __restrict__ out /*[B][2][N]*/, size_t B) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * 2 * F1::N) return;
+    const size_t m = e / (2 * F1::N), w = e % (2 * F1::N);
+    u32 s = 0;
+#pragma unroll
+    for (int c = 0; c < CLUE_COUNT; ++c) s += in[(m * CLUE_COUNT + c) * 2 * F1::N + w];    // 7q < 2^30
+    out[e] = s % Q1;
 }
 
 // ---- K3: second-level blind rotation, transforms and MAC on the FP64 pipe (D2 in field.cuh) -----------------------------
-// One CTA (256 threads, 8 coefficients each) per message.  acc stays canonical u64 in shared memory (decomposition is
+// One CTA (256 threads, 8 coefficients each) per message, two CTAs per SM.  acc stays canonical u64 in shared memory (decomposition is
 // integer bit work); digits enter the NTT as doubles, two digits per pass (shared barriers, twice the ILP); key words are
 // centred doubles already multiplied by N^-1, streamed from L2 with L1::no_allocate so the twiddle tables stay in L1;
 // the MAC accumulators are 16 doubles.
 constexpr int L2_THREADS = GeoL2::NT;
-constexpr size_t L2_SMEM = (size_t)2 * F2::N * 8 + (size_t)4 * GeoL2::BUF * 8 + 672 * sizeof(unsigned short);
+constexpr size_t L2_SMEM = (size_t)2 * F2::N * 8 + (size_t)2 * GeoL2::BUF * 8 + F2::N * sizeof(double2) + 672 * sizeof(unsigned short);
 
 __device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
     double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
 
@@ -229,10 +242,11 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
     constexpr int N = F::N, E = GEO::E, L = G::LEVELS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* acc = reinterpret_cast<u64*>(smem_raw);
-    double* bufs = reinterpret_cast<double*>(acc + 2 * N);
-    ExBuf<double> e0{bufs, bufs + GEO::BUF}, e1{bufs + 2 * GEO::BUF, bufs + 3 * GEO::BUF};
-    unsigned short* la = reinterpret_cast<unsigned short*>(bufs + 4 * GEO::BUF);
+    double* bx = reinterpret_cast<double*>(acc + 2 * N); double* by = bx + GEO::BUF;
+    double2* s_tw = reinterpret_cast<double2*>(by + GEO::BUF);          // forward twiddles: the L1 cache left beside 2 x 100 KiB
+    unsigned short* la = reinterpret_cast<unsigned short*>(s_tw + N);   // of shared memory is too small to hold them
     const int msg = blockIdx.x, t = threadIdx.x;
+    for (int i = t; i < N; i += L2_THREADS) s_tw[i] = tb.tw2d[i];
     for (int i = t; i < LWE2_STRIDE_IN; i += L2_THREADS) la[i] = (unsigned short)lwe[(size_t)msg * LWE2_STRIDE_IN + i];
     __syncthreads();
     init_acc<F, GEO>(acc, tb.lut2, la[LWE2_N], t);
@@ -257,7 +271,7 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
                     x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r));
                     y[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r + 1));
                 }
-                ntt_forward2<AR, GEO, LdGlobal>(x, y, e0, e1, tb.tw2d, t, 0);
+                ntt_forward2s<AR, GEO, LdShared>(x, y, bx, by, s_tw, t, 0);
                 const double* kx = key + (size_t)(p * L + r) * 2 * N;         // rows r and r+1: [a | b] each
 #pragma unroll
                 for (int k = 0; k < E; k += 2) {
@@ -274,7 +288,7 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
         }
 #pragma unroll
         for (int k = 0; k < E; ++k) { ma[k] = D2::renorm(ma[k]); mb[k] = D2::renorm(mb[k]); }
-        ntt_inverse2<AR, GEO, LdGlobal>(ma, mb, e0, e1, tb.itw2d, t, 0);
+        ntt_inverse2s<AR, GEO, LdGlobal>(ma, mb, bx, by, tb.itw2d, t, 0);
 #pragma unroll
         for (int k = 0; k < E; ++k) {
             const int pos = t + GEO::NT * k;

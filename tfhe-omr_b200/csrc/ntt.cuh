@@ -257,6 +257,47 @@ __device__ __forceinline__ void ntt_inverse2(typename AR::T (&x)[GEO::E], typena
     inv_pass<AR, GEO, 0, LD>(x, itw, t); inv_pass<AR, GEO, 0, LD>(y, itw, t);
 }
 
+// Two transforms through only TWO buffers (x always via `bx`, y always via `by`), staggered so that every store to a
+// buffer is separated from the previous loads of it by a barrier: store x | bar | load x, store y | bar | load y.
+template <class AR, class GEO, int P, int X, class T>
+__device__ __forceinline__ void exchange2s(T (&x)[GEO::E], T (&y)[GEO::E], T* bx, T* by, int t, int bar) {
+    ex_store<GEO, P, X>(x, bx, t); group_sync<GEO::NT>(bar);
+    ex_load<GEO, P + 1, X>(x, bx, t); ex_store<GEO, P, X>(y, by, t); group_sync<GEO::NT>(bar);
+    ex_load<GEO, P + 1, X>(y, by, t);
+}
+template <class AR, class GEO, int P, int X, class T>
+__device__ __forceinline__ void exchange2s_inv(T (&x)[GEO::E], T (&y)[GEO::E], T* bx, T* by, int t, int bar) {
+    ex_store<GEO, P + 1, X>(x, bx, t); group_sync<GEO::NT>(bar);
+    ex_load<GEO, P, X>(x, bx, t); ex_store<GEO, P + 1, X>(y, by, t); group_sync<GEO::NT>(bar);
+    ex_load<GEO, P, X>(y, by, t);
+}
+template <class AR, class GEO, class LD>
+__device__ __forceinline__ void ntt_forward2s(typename AR::T (&x)[GEO::E], typename AR::T (&y)[GEO::E], typename AR::T* bx, typename AR::T* by,
+                                              const typename AR::TW* __restrict__ tw, int t, int bar) {
+    fwd_pass<AR, GEO, 0, LD>(x, tw, t); fwd_pass<AR, GEO, 0, LD>(y, tw, t);
+    exchange2s<AR, GEO, 0, 0>(x, y, bx, by, t, bar);
+    fwd_pass<AR, GEO, 1, LD>(x, tw, t); fwd_pass<AR, GEO, 1, LD>(y, tw, t);
+    exchange2s<AR, GEO, 1, 1>(x, y, bx, by, t, bar);
+    fwd_pass<AR, GEO, 2, LD>(x, tw, t); fwd_pass<AR, GEO, 2, LD>(y, tw, t);
+    if constexpr (GEO::NPASS == 4) {
+        exchange2s<AR, GEO, 2, 2>(x, y, bx, by, t, bar);
+        fwd_pass<AR, GEO, 3, LD>(x, tw, t); fwd_pass<AR, GEO, 3, LD>(y, tw, t);
+    }
+}
+template <class AR, class GEO, class LD>
+__device__ __forceinline__ void ntt_inverse2s(typename AR::T (&x)[GEO::E], typename AR::T (&y)[GEO::E], typename AR::T* bx, typename AR::T* by,
+                                              const typename AR::TW* __restrict__ itw, int t, int bar) {
+    if constexpr (GEO::NPASS == 4) {
+        inv_pass<AR, GEO, 3, LD>(x, itw, t); inv_pass<AR, GEO, 3, LD>(y, itw, t);
+        exchange2s_inv<AR, GEO, 2, 2>(x, y, bx, by, t, bar);
+    }
+    inv_pass<AR, GEO, 2, LD>(x, itw, t); inv_pass<AR, GEO, 2, LD>(y, itw, t);
+    exchange2s_inv<AR, GEO, 1, 1>(x, y, bx, by, t, bar);
+    inv_pass<AR, GEO, 1, LD>(x, itw, t); inv_pass<AR, GEO, 1, LD>(y, itw, t);
+    exchange2s_inv<AR, GEO, 0, 0>(x, y, bx, by, t, bar);
+    inv_pass<AR, GEO, 0, LD>(x, itw, t); inv_pass<AR, GEO, 0, LD>(y, itw, t);
+}
+
 // index of element k of thread t after the forward transform (= NTT-domain coefficient index, bit-reversed order)
 template <class GEO> __host__ __device__ constexpr int out_idx(int t, int k) { return Pass<GEO, GEO::NPASS - 1>::idx(t, k); }
 
