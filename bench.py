@@ -30,6 +30,7 @@ README_SINGLE_CORE_MSGS = 65536 / 15340.2083335          # /root/reference READM
 # algorithmic work per message
 M32 = 242_221_056          # 32-bit mulmods (L1 blind rotations)
 M64 = 143_082_496          # 64-bit mulmods (L2 blind rotation + trace + final NTTs)
+M64_L2 = 138_588_160       # ... of which the L2 blind rotation
 BSK2_BYTES = 670 * 12 * 2 * 2048 * 8
 
 
@@ -208,14 +209,19 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- rooflines for the dominant kernel (L2 blind rotation; ~2/3 of the step) -------------------------------------
+    # ---- rooflines ---------------------------------------------------------------------------------------------------
+    # dominant kernel = l2_blind_rotate_kernel (FP64 pipe) with l1_blind_rotate_kernel (integer pipes) a close second.
+    # `roofline` is the HBM view the contract asks for (algorithmic bytes / kernel time vs measured copy bandwidth): it is
+    # tiny by design — the key pass is shared by the whole launch — and `roofline_compute` is the bound that binds:
+    # mulmods/s of each kernel against the measured peak of the register-only butterfly loop on the same pipe.
     peaks, peak_src = _peaks()
     l2_ms = times.total_second_level_bootstrapping_time / args.steps          # CUDA events on the launching stream
     l1_ms = times.total_first_level_bootstrapping_time / args.steps
+    tr_ms = times.total_trace_time / args.steps
     alg_bytes = BSK2_BYTES + M * (671 * 4 + 2 * 2048 * 8)                     # key pass once per launch + LWE in + RLWE out
     hbm_achieved = alg_bytes / (l2_ms * 1e-3) / 1e9
-    p32 = det.mulmod_peak(1); p64 = det.mulmod_peak(2)
-    t_roof = M32 / p32 + M64 / p64                                            # seconds per message at the measured integer peak
+    p32 = det.mulmod_peak(1); p64i = det.mulmod_peak(2); p64f = det.mulmod_peak(3)
+    t_roof = M32 / p32 + M64 / p64f                                           # seconds per message at the measured peaks
     t_meas = ms_per_step * 1e-3 / M
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "messages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -230,14 +236,22 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "l2_blind_rotate_kernel", "achieved": round(hbm_achieved, 3), "peak": peaks.get("hbm_gbs"),
-                     "unit": "GB/s", "frac": round(hbm_achieved / peaks.get("hbm_gbs"), 6), "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(hbm_achieved / peaks.get("hbm_gbs"), 6), "traffic": args.l2_traffic_bytes, "peak_source": peak_src,
                      "kernel_ms_per_launch": round(l2_ms, 3), "kernel_share_of_step": round(l2_ms / ms_per_step, 3),
-                     "note": "integer-issue bound, not HBM bound: see roofline_int"},
-        "roofline_int": {"bound": "int-pipe", "achieved": round(1.0 / t_meas, 1), "peak": round(1.0 / t_roof, 1), "unit": "messages/s/GPU",
-                         "frac": round(t_roof / t_meas, 4), "peak_mulmod32_per_s": p32, "peak_mulmod64_per_s": p64,
-                         "per_message": {"mulmod32": M32, "mulmod64": M64},
-                         "stage_ms_per_step": {"first_level": round(l1_ms, 2), "second_level": round(l2_ms, 2),
-                                               "trace": round(times.total_trace_time / args.steps, 2)}},
+                     "note": "compute bound (FP64 / integer issue), not HBM bound: see roofline_compute"},
+        "roofline_compute": {
+            "bound": "fp64+int pipes", "achieved": round(1.0 / t_meas, 1), "peak": round(1.0 / t_roof, 1), "unit": "messages/s/GPU",
+            "frac": round(t_roof / t_meas, 4),
+            "kernels": {
+                "l1_blind_rotate_kernel": {"pipe": "int (IMAD/IMAD.HI)", "mulmod_per_s": round(M32 * M / (l1_ms * 1e-3)), "peak_mulmod_per_s": round(p32),
+                                           "frac": round(M32 * M / (l1_ms * 1e-3) / p32, 4), "ms_per_launch": round(l1_ms, 2)},
+                "l2_blind_rotate_kernel": {"pipe": "fp64 (DFMA, exact error-free mulmod)", "mulmod_per_s": round(M64_L2 * M / (l2_ms * 1e-3)),
+                                           "peak_mulmod_per_s": round(p64f), "frac": round(M64_L2 * M / (l2_ms * 1e-3) / p64f, 4),
+                                           "ms_per_launch": round(l2_ms, 2)},
+            },
+            "peaks_measured": {"int32_butterfly_per_s": p32, "int64_butterfly_per_s": p64i, "fp64_butterfly_per_s": p64f},
+            "per_message": {"mulmod32": M32, "mulmod64": M64},
+            "stage_ms_per_step": {"first_level": round(l1_ms, 2), "second_level": round(l2_ms, 2), "trace": round(tr_ms, 2)}},
     }
     if key_host is not None:
         line["cpu_baseline"] = cpu_baseline(key_host, args)
@@ -321,9 +335,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2-traffic-bytes", type=float, default=None, help="dram bytes per l2_blind_rotate launch from an ncu --set full capture")
     args = ap.parse_args()
     if D_BOARD % args.messages_per_step:
         raise SystemExit("--messages-per-step must divide 65536")
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: not launched by torchrun -> re-launch ourselves under it (one rank per GPU, NCCL)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args)
     else:

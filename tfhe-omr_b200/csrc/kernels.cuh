@@ -601,54 +601,52 @@ __global__ void ksk_pad_kernel(const u32* __restrict__ in, u32* __restrict__ out
     out[i] = c < (size_t)LWE2_STRIDE_IN ? in[r * LWE2_STRIDE_IN + c] : 0u;
 }
 
-// ---- step-0 peak: register-only loop of the Shoup butterfly the NTTs use (the denominator of the integer roofline) --
-// every thread runs 8 independent forward butterflies per iteration (= 8 mulmods + their add/sub), no memory traffic.
+// ---- step-0 peaks: register-only loops of exactly the forward butterfly the transforms are made of (no memory traffic,
+// 8 independent butterflies per thread per iteration) — the denominators of the compute roofline in bench.py.
 template <class F>
 __global__ void __launch_bounds__(256) mulmod_peak_kernel(typename F::T* sink, typename F::TW w0, int iters) {
     typedef typename F::T T;
-    T x[8];
+    T x[16];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = (T)(threadIdx.x * 8 + k + 1);
+    for (int k = 0; k < 16; ++k) x[k] = (T)(threadIdx.x * 16 + k + 1);
     typename F::TW w = w0;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            T u = x[k], v = F::mul_shoup(x[k + 4], w);
-            x[k] = u + v; x[k + 4] = u - v + 2 * F::Q;
+        for (int k = 0; k < 8; ++k) {                              // Harvey/Shoup: IMAD.HI + 2 IMAD + 2 adds, never reduced
+            T u = x[k], v = F::mul_shoup(x[k + 8], w);
+            x[k] = u + v; x[k + 8] = u - v + 2 * F::Q;
         }
+        if ((it & 7) == 7) {
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            T u = x[k], v = F::mul_shoup(x[k + 1], w);
-            x[k] = F::canon_lazy(u + v); x[k + 1] = F::canon_lazy(u - v + 2 * F::Q);
+            for (int k = 0; k < 16; ++k) x[k] = F::canon_lazy(x[k] & (T)(((T)1 << (F::QBITS + 4)) - 1));
         }
     }
     T acc = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += x[k];
+    for (int k = 0; k < 16; ++k) acc += x[k];
     if (acc == (T)0x12345) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
-// the same loop with the FP64 butterfly of the level-2 kernel (6-op exact mulmod + add/sub)
+// the FP64 butterfly of the level-2 kernel: 6-op exact mulmod + add/sub = 8 DP instructions
 __global__ void __launch_bounds__(256) mulmod_peak_f64_kernel(double* sink, double2 w, int iters) {
-    double x[8];
+    double x[16];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = (double)(threadIdx.x * 8 + k + 1);
+    for (int k = 0; k < 16; ++k) x[k] = (double)(threadIdx.x * 16 + k + 1);
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const double u = x[k], v = D2::mulmod(x[k + 4], w.x, w.y);
-            x[k] = __dadd_rn(u, v); x[k + 4] = __dadd_rn(u, -v);
+        for (int k = 0; k < 8; ++k) {
+            const double u = x[k], v = D2::mulmod(x[k + 8], w.x, w.y);
+            x[k] = __dadd_rn(u, v); x[k + 8] = __dadd_rn(u, -v);
         }
+        if ((it & 3) == 3) {
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            const double u = D2::renorm(x[k]), v = D2::mulmod(x[k + 1], w.x, w.y);
-            x[k] = __dadd_rn(u, v); x[k + 1] = __dadd_rn(u, -v);
+            for (int k = 0; k < 16; ++k) x[k] = D2::renorm(x[k]);
         }
     }
     double acc = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += x[k];
+    for (int k = 0; k < 16; ++k) acc += x[k];
     if (acc == 12345.0) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
