@@ -128,7 +128,7 @@ int launch_l1(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, 
 int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s) {
     if (!B) return OMR_OK;
     dim3 grid((unsigned)((B + KS_MB - 1) / KS_MB), (KSK_PAD + KS_THREADS - 1) / KS_THREADS);
-    keyswitch_kernel<<<grid, KS_THREADS, 0, s>>>(rlwe, ctx->ksk, out, (int)B);
+    keyswitch_kernel<<<grid, KS_THREADS, KS_SMEM, s>>>(rlwe, ctx->ksk, out, (int)B);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
@@ -370,6 +370,7 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     ctx->l1_half = getenv("OMR_L1_HALF") != nullptr;
     if (const char* e = getenv("OMR_OVERLAP")) ctx->overlap = atoi(e) != 0;
     if (const char* e = getenv("OMR_CHUNK")) { long v = atol(e); if (v >= 8) ctx->chunk = (size_t)v; }
+    CKC(cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
     CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2_SMEM));
     CKC(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM));
     // keys -> internal form: every ring word * (R * N^-1) mod q; KSK padded to a 672-word row stride

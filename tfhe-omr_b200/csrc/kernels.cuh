@@ -207,13 +207,9 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
         for (int k = 0; k < E; ++k) { ya[k] = F::inv_prepare(F::redc(ma[k])); yb[k] = F::inv_prepare(F::redc(mb[k])); }
         __syncthreads();                                                         // every group is done with tile i
         if (threadIdx.x == 0 && i + 1 < CLUE_N) tma_load(ktile, bsk1 + (size_t)(i + 1) * L1_TILE_WORDS, CFG::TILE_WORDS * 4, mbar);
-        if (HALF) {
-            ntt_inverse<AR, GEO, LdGlobal>(ya, eb, tb.itw1, t, bar);
-            ntt_inverse<AR, GEO, LdGlobal>(yb, eb, tb.itw1, t, bar);
-        } else {
-            ntt_inverse<AR, GEO, LdShared>(ya, eb, s_itw_smem, t, bar);
-            ntt_inverse<AR, GEO, LdShared>(yb, eb, s_itw_smem, t, bar);
-        }
+        // both inverse transforms in flight (two buffers, staggered exchanges): twice the ILP of running them back to back
+        if (HALF) ntt_inverse2s<AR, GEO, LdGlobal>(ya, yb, eb.a, eb.b, tb.itw1, t, bar);
+        else ntt_inverse2s<AR, GEO, LdShared>(ya, yb, eb.a, eb.b, s_itw_smem, t, bar);
 #pragma unroll
         for (int k = 0; k < E; ++k) {
             const int pos = t + GEO::NT * k;
@@ -323,11 +319,13 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
 // out[col] = (0,..,0,b0) - SUM_{i<1024, j<27} d_ij * KSK[i][j][col]  (d = balanced base-2 digits of a'_i), then
 // x -> round(x * 4096 / q1) mod 4096, b += 7 * 128.   A {-1,0,1} x u32 integer product: thread = column,
 // KS_MB messages per CTA share each key row load.
-constexpr int KS_MB = 8, KS_THREADS = 128;
+constexpr int KS_MB = 16, KS_THREADS = 128;
+constexpr size_t KS_SMEM = (size_t)KS_MB * F1::N * sizeof(i32);
 
 __global__ void __launch_bounds__(KS_THREADS)
 keyswitch_kernel(const u32* __restrict__ rlwe, const u32* __restrict__ ksk, u32* __restrict__ out, int B) {
-    __shared__ i32 uw[KS_MB][F1::N];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    i32 (*uw)[F1::N] = reinterpret_cast<i32 (*)[F1::N]>(smem_raw);        // [KS_MB][N] offset words
     const int m0 = blockIdx.x * KS_MB, col = blockIdx.y * KS_THREADS + threadIdx.x;
     for (int e = threadIdx.x; e < KS_MB * F1::N; e += KS_THREADS) {
         const int m = e / F1::N, i = e % F1::N;
