@@ -32,6 +32,7 @@ M32 = 242_221_056          # 32-bit mulmods (L1 blind rotations)
 M64 = 143_082_496          # 64-bit mulmods (L2 blind rotation + trace + final NTTs)
 M64_L2 = 138_588_160       # ... of which the L2 blind rotation
 BSK2_BYTES = 670 * 12 * 2 * 2048 * 8
+L2_TRAFFIC_8192 = 16195931648 + 236123392   # dram__bytes_read.sum + dram__bytes_write.sum, l2_blind_rotate_kernel, B = 8192
 
 
 def _peaks():
@@ -220,9 +221,19 @@ def run_ours(args):
     tr_ms = times.total_trace_time / args.steps
     alg_bytes = BSK2_BYTES + M * (671 * 4 + 2 * 2048 * 8)                     # key pass once per launch + LWE in + RLWE out
     hbm_achieved = alg_bytes / (l2_ms * 1e-3) / 1e9
-    p32 = det.mulmod_peak(1); p64i = det.mulmod_peak(2); p64f = det.mulmod_peak(3)
-    t_roof = M32 / p32 + M64 / p64f                                           # seconds per message at the measured peaks
-    t_meas = ms_per_step * 1e-3 / M
+    traffic, traffic_src = args.l2_traffic_bytes, "command line"
+    if traffic is None and M == 8192:                                         # ncu capture of this launch shape, round 1
+        traffic, traffic_src = L2_TRAFFIC_8192, "profiles/r1_dram_traffic_blind_rotate_batch8192.csv (dram read+write, one launch of 8192 CTAs)"
+    elif traffic is None:
+        traffic_src = None
+    # peaks: (1) pipe ceilings from the measured issue rates on this pool's B200 (profiles/r1_pipe_microbench.txt:
+    # IMAD 64, IMAD.HI 27.2, DFMA/DADD/DMUL 64 lane-ops/clk/SM) at the SM clock sampled during the timed region;
+    # (2) the register-only butterfly loops of the library (omr_mulmod_peak) as a cross-check.
+    sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    p32 = n_sm * sm_clk * 64.0 / (64.0 / 27.2 + 2.0)          # int butterfly: IMAD.HI + 2 IMAD on the fma pipe
+    p64f = n_sm * sm_clk * 64.0 / 8.0                         # fp64 butterfly: 8 DP instructions
+    loop32 = det.mulmod_peak(1); loop64i = det.mulmod_peak(2); loop64f = det.mulmod_peak(3)
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "messages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
@@ -236,7 +247,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "l2_blind_rotate_kernel", "achieved": round(hbm_achieved, 3), "peak": peaks.get("hbm_gbs"),
-                     "unit": "GB/s", "frac": round(hbm_achieved / peaks.get("hbm_gbs"), 6), "traffic": args.l2_traffic_bytes, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(hbm_achieved / peaks.get("hbm_gbs"), 6), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel_ms_per_launch": round(l2_ms, 3), "kernel_share_of_step": round(l2_ms / ms_per_step, 3),
                      "note": "compute bound (FP64 / integer issue), not HBM bound: see roofline_compute"},
         "roofline_compute": {
@@ -244,12 +255,14 @@ def run_ours(args):
             "frac": round(t_roof / t_meas, 4),
             "kernels": {
                 "l1_blind_rotate_kernel": {"pipe": "int (IMAD/IMAD.HI)", "mulmod_per_s": round(M32 * M / (l1_ms * 1e-3)), "peak_mulmod_per_s": round(p32),
-                                           "frac": round(M32 * M / (l1_ms * 1e-3) / p32, 4), "ms_per_launch": round(l1_ms, 2)},
+                                           "frac": round(M32 * M / (l1_ms * 1e-3) / p32, 4), "ms_per_launch": round(l1_ms, 2),
+                                           "register_loop_mulmod_per_s": round(loop32)},
                 "l2_blind_rotate_kernel": {"pipe": "fp64 (DFMA, exact error-free mulmod)", "mulmod_per_s": round(M64_L2 * M / (l2_ms * 1e-3)),
                                            "peak_mulmod_per_s": round(p64f), "frac": round(M64_L2 * M / (l2_ms * 1e-3) / p64f, 4),
-                                           "ms_per_launch": round(l2_ms, 2)},
+                                           "ms_per_launch": round(l2_ms, 2), "register_loop_mulmod_per_s": round(loop64f)},
             },
-            "peaks_measured": {"int32_butterfly_per_s": p32, "int64_butterfly_per_s": p64i, "fp64_butterfly_per_s": p64f},
+            "peak_source": "issue rates measured on this pool (profiles/r1_pipe_microbench.txt) x sampled SM clock",
+            "register_loops": {"int32_butterfly_per_s": loop32, "int64_butterfly_per_s": loop64i, "fp64_butterfly_per_s": loop64f},
             "per_message": {"mulmod32": M32, "mulmod64": M64},
             "stage_ms_per_step": {"first_level": round(l1_ms, 2), "second_level": round(l2_ms, 2), "trace": round(tr_ms, 2)}},
     }
