@@ -234,6 +234,8 @@ def run_ours(args):
     p32 = n_sm * sm_clk * 64.0 / (64.0 / 27.2 + 2.0)          # int butterfly: IMAD.HI + 2 IMAD on the fma pipe
     p64f = n_sm * sm_clk * 64.0 / 8.0                         # fp64 butterfly: 8 DP instructions
     loop32 = det.mulmod_peak(1); loop64i = det.mulmod_peak(2); loop64f = det.mulmod_peak(3)
+    t_roof = M32 / p32 + M64 / p64f                                           # seconds per message at the pipe ceilings
+    t_meas = ms_per_step * 1e-3 / M                                           # seconds per message per GPU, measured
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "messages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
