@@ -207,6 +207,24 @@ template <class T> struct NttTable {
         }
     }
 
+    // forward without the final canonicalisation: output in [0, 4q)
+    void forward_lazy(T* a) const {
+        const T two_q = 2 * q;
+        int t = n;
+        for (int m = 1; m < n; m <<= 1) {
+            t >>= 1;
+            for (int i = 0; i < m; ++i) {
+                const T w = tw[m + i], ws = tw_shoup[m + i];
+                T* x = a + 2 * i * t; T* y = x + t;
+                for (int j = 0; j < t; ++j) {
+                    T u = x[j]; u = u >= two_q ? u - two_q : u;
+                    T v = mul_shoup(y[j], w, ws, q);
+                    x[j] = u + v; y[j] = u - v + two_q;
+                }
+            }
+        }
+    }
+
     // in-place inverse; input in [0,2q), output canonical [0,q)
     void inverse(T* a) const {
         const T two_q = 2 * q;
@@ -515,9 +533,10 @@ template <class T> inline void monomial_mul(const T* p, int n, unsigned k, T q, 
     }
 }
 
-// One CMux step: acc += ((X^a - 1) * acc) [x] RGSW.  SURVEY A.5 step 2.
+// One CMux step: acc += ((X^a - 1) * acc) [x] RGSW.  SURVEY A.5 step 2.  Plain form (the specification; the
+// production form below is checked against it in tests/test_oracle_primitives.py).
 template <class T>
-inline void cmux_step(const NttTable<T>& tab, T* acc_a, T* acc_b, unsigned a, const T* rgsw /*[2L][2][n]*/,
+inline void cmux_step_simple(const NttTable<T>& tab, T* acc_a, T* acc_b, unsigned a, const T* rgsw /*[2L][2][n]*/,
                       int logb, int levels, int drop) {
     const int n = tab.n; const T q = tab.q;
     using W = typename Wide<T>::type;
@@ -545,6 +564,51 @@ inline void cmux_step(const NttTable<T>& tab, T* acc_a, T* acc_b, unsigned a, co
     for (int i = 0; i < n; ++i) { ta[i] = (T)(sa[i] % q); tb_[i] = (T)(sb[i] % q); }
     tab.inverse(ta.data()); tab.inverse(tb_.data());
     for (int i = 0; i < n; ++i) { acc_a[i] = addmod(acc_a[i], ta[i], q); acc_b[i] = addmod(acc_b[i], tb_[i], q); }
+}
+
+// Production form of the same step for the CPU baseline: no allocation, offset-word digit extraction (one centred word
+// per coefficient, digits by shift/mask, top digit absorbs the remainder — identical digits to gadget_decompose), lazy
+// forward transforms (< 4q into the multiply-accumulate) and the special-form reduction for q2.
+template <class T> struct CmuxWs { std::vector<T> ta, tb, dig; std::vector<typename Wide<T>::type> sa, sb; std::vector<i64> wa, wb;
+    void ensure(int n) { if ((int)ta.size() != n) { ta.resize(n); tb.resize(n); dig.resize(n); sa.resize(n); sb.resize(n); wa.resize(n); wb.resize(n); } } };
+template <class T> inline T reduce_acc(typename Wide<T>::type v, T q);
+template <> inline u32 reduce_acc<u32>(u64 v, u32 q) { return (u32)(v % q); }
+template <> inline u64 reduce_acc<u64>(u128 v, u64) { return reduce128_q2(v); }
+template <class T>
+inline void cmux_step(const NttTable<T>& tab, T* acc_a, T* acc_b, unsigned a, const T* rgsw /*[2L][2][n]*/,
+                      int logb, int levels, int drop) {
+    const int n = tab.n; const T q = tab.q;
+    using W = typename Wide<T>::type;
+    if (a == 0) return;                                     // (X^0 - 1) = 0: bit-identical to not skipping
+    static thread_local CmuxWs<T> ws; ws.ensure(n);
+    monomial_mul(acc_a, n, a, q, ws.ta.data()); monomial_mul(acc_b, n, a, q, ws.tb.data());
+    i64 off = 0;
+    for (int j = 0; j < levels - 1; ++j) off += ((i64)1 << (logb - 1)) << (logb * j);
+    const i64 half_q = (i64)(q >> 1), rnd = drop > 0 ? (i64)1 << (drop - 1) : 0;
+    for (int i = 0; i < n; ++i) {
+        i64 va = (i64)submod(ws.ta[i], acc_a[i], q), vb = (i64)submod(ws.tb[i], acc_b[i], q);
+        if (va > half_q) va -= (i64)q;
+        if (vb > half_q) vb -= (i64)q;
+        ws.wa[i] = ((va + rnd) >> drop) + off; ws.wb[i] = ((vb + rnd) >> drop) + off;
+        ws.sa[i] = 0; ws.sb[i] = 0;
+    }
+    const i64 mask = ((i64)1 << logb) - 1, hb = (i64)1 << (logb - 1);
+    for (int half = 0; half < 2; ++half) {
+        const i64* wsrc = half ? ws.wb.data() : ws.wa.data();
+        for (int j = 0; j < levels; ++j) {
+            T* x = ws.dig.data();
+            if (j < levels - 1) for (int i = 0; i < n; ++i) { i64 d = ((wsrc[i] >> (logb * j)) & mask) - hb; x[i] = (T)(d < 0 ? (i64)q + d : d); }
+            else for (int i = 0; i < n; ++i) { i64 d = wsrc[i] >> (logb * (levels - 1)); x[i] = (T)(d < 0 ? (i64)q + d : d); }
+            tab.forward_lazy(x);
+            const T* ka = rgsw + ((size_t)(half * levels + j) * 2 + 0) * n;
+            const T* kb = ka + n;
+            W* sa = ws.sa.data(); W* sb = ws.sb.data();
+            for (int i = 0; i < n; ++i) { sa[i] += (W)x[i] * ka[i]; sb[i] += (W)x[i] * kb[i]; }
+        }
+    }
+    for (int i = 0; i < n; ++i) { ws.ta[i] = reduce_acc<T>(ws.sa[i], q); ws.tb[i] = reduce_acc<T>(ws.sb[i], q); }
+    tab.inverse(ws.ta.data()); tab.inverse(ws.tb.data());
+    for (int i = 0; i < n; ++i) { acc_a[i] = addmod(acc_a[i], ws.ta[i], q); acc_b[i] = addmod(acc_b[i], ws.tb[i], q); }
 }
 
 // BlindRotationKey::blind_rotate [UPSTREAM] — detector.rs:555, 623.  acc = (0, LUT * X^(2N - b)).

@@ -148,6 +148,15 @@ void orc_cmux1(void* hh, uint32_t* acc /*[2][1024]*/, unsigned a, int key_index)
     auto* h = (OrcHandle*)hh;
     cmux_step<u32>(tables().t1, acc, acc + N1, a, h->dk.bsk1.data() + (size_t)key_index * BSK1_ROWS * 2 * N1, BS1_LOGB, BS1_LEVELS, BS1_DROP);
 }
+// the plain (specification) form of the same step, for checking the production form against it
+void orc_cmux1_simple(void* hh, uint32_t* acc, unsigned a, int key_index) {
+    auto* h = (OrcHandle*)hh;
+    cmux_step_simple<u32>(tables().t1, acc, acc + N1, a, h->dk.bsk1.data() + (size_t)key_index * BSK1_ROWS * 2 * N1, BS1_LOGB, BS1_LEVELS, BS1_DROP);
+}
+void orc_cmux2_simple(void* hh, uint64_t* acc, unsigned a, int key_index) {
+    auto* h = (OrcHandle*)hh;
+    cmux_step_simple<u64>(tables().t2, acc, acc + N2, a, h->dk.bsk2.data() + (size_t)key_index * BSK2_ROWS * 2 * N2, BS2_LOGB, BS2_LEVELS, BS2_DROP);
+}
 void orc_cmux2(void* hh, uint64_t* acc /*[2][2048]*/, unsigned a, int key_index) {
     auto* h = (OrcHandle*)hh;
     cmux_step<u64>(tables().t2, acc, acc + N2, a, h->dk.bsk2.data() + (size_t)key_index * BSK2_ROWS * 2 * N2, BS2_LOGB, BS2_LEVELS, BS2_DROP);

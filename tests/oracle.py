@@ -64,6 +64,8 @@ def lib(native=False):
     L.orc_trace.argtypes = [vp, vp, sz, i32]
     L.orc_cmux1.argtypes = [vp, vp, C.c_uint, i32]
     L.orc_cmux2.argtypes = [vp, vp, C.c_uint, i32]
+    L.orc_cmux1_simple.argtypes = [vp, vp, C.c_uint, i32]
+    L.orc_cmux2_simple.argtypes = [vp, vp, C.c_uint, i32]
     L.orc_encode_indices.argtypes = [sz, i32, vp, sz, u64, u64, u32, vp]
     L.orc_encode_payloads.argtypes = [vp, vp, sz, u64, vp, sz, i32, i32, vp, i32]
     L.orc_decrypt_decode.argtypes = [vp, vp, vp]
@@ -187,6 +189,12 @@ class KeyPack:
 
     def cmux2(self, acc, a, key_index):
         acc = np.array(acc, np.uint64).reshape(2, N2); self.L.orc_cmux2(self.h, ptr(acc), a, key_index); return acc
+
+    def cmux1_simple(self, acc, a, key_index):
+        acc = np.array(acc, np.uint32).reshape(2, N1); self.L.orc_cmux1_simple(self.h, ptr(acc), a, key_index); return acc
+
+    def cmux2_simple(self, acc, a, key_index):
+        acc = np.array(acc, np.uint64).reshape(2, N2); self.L.orc_cmux2_simple(self.h, ptr(acc), a, key_index); return acc
 
     def decrypt_decode(self, ct):
         ct = np.ascontiguousarray(ct, np.uint64); out = np.zeros(N2, np.uint64)

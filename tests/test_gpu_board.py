@@ -135,3 +135,28 @@ def test_small_boards_index_zero_and_collisions(detector, keypack):
         st, found, solved = keypack.decode_digest(Dn, Dn, ih, ph, weights)
         assert st == 0 and list(found) == list(range(Dn))
         assert np.array_equal(solved, payloads)
+
+
+def test_determinism_and_scheduling_independence():
+    """compute-sanitizer is closed on this pool, so shared-memory hazards are hunted the other way round: 1 184 random
+    messages (8 waves of co-resident CTAs) must give identical bits on every run and for every split of the batch."""
+    import torch
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from stage_times import random_detector
+    det = random_detector(seed=3)
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    B = 1184
+    a = torch.randint(0, 2048, (B, 512), dtype=torch.int16, device="cuda", generator=g)
+    b = torch.randint(0, 2048, (B, 7), dtype=torch.int16, device="cuda", generator=g)
+    ref = det.detect((a, b)).tensor
+    again = det.detect((a, b)).tensor
+    assert torch.equal(ref, again)
+    parts = torch.cat([det.detect((a[:301], b[:301])).tensor, det.detect((a[301:], b[301:])).tensor])
+    assert torch.equal(ref, parts)
+    # a spot check of the same batch against the oracle (random keys are legitimate inputs: the path is data-oblivious)
+    bsk1, ksk, bsk2, trk = (t.cpu().numpy() for t in det.detection_key.__dict__.values() if hasattr(t, "cpu"))
+    kp = O.KeyPack(blobs=(bsk1.view(np.uint32), ksk.view(np.uint32), bsk2.view(np.uint64), trk.view(np.uint64)))
+    pick = [0, 592, 1183]
+    want = kp.detect(a[pick].cpu().numpy().view(np.uint16), b[pick].cpu().numpy().view(np.uint16), threads=3)
+    assert np.array_equal(ref[pick].cpu().numpy().view(np.uint64), want)

@@ -109,3 +109,15 @@ def test_bucket_hash_uniform():
     b = np.array([O.lib().orc_bucket_of(5, 1, m, 2) for m in range(20000)])
     assert b.min() == 0 and b.max() == 129
     assert np.bincount(b, minlength=130).min() > 100
+
+
+def test_production_cmux_equals_plain_cmux():
+    """the allocation-free / lazy / special-form CMux used for the CPU baseline computes exactly the plain one"""
+    kp = O.KeyPack(blobs=O.random_key_blobs(5))
+    rng = np.random.default_rng(8)
+    for a in (1, 777, 1024, 2047):
+        acc = rng.integers(0, O.Q1, (2, 1024), dtype=np.uint32)
+        assert np.array_equal(kp.cmux1(acc, a, 3), kp.cmux1_simple(acc, a, 3))
+    for a in (1, 1500, 2048, 4095):
+        acc = rng.integers(0, O.Q2, (2, 2048), dtype=np.uint64)
+        assert np.array_equal(kp.cmux2(acc, a, 5), kp.cmux2_simple(acc, a, 5))
