@@ -140,7 +140,7 @@ int launch_l2(omr_ctx* ctx, const u32* lwe, size_t B, u64* out, cudaStream_t s) 
 }
 int launch_trace(omr_ctx* ctx, u64* ct, size_t B, cudaStream_t s) {
     if (!B) return OMR_OK;
-    trace_kernel<<<(unsigned)B, TR_THREADS, TR_SMEM, s>>>(ct, ctx->trk, ctx->tb);
+    trace_kernel<<<(unsigned)B, TR_THREADS, TR_SMEM, s>>>(ct, reinterpret_cast<const double*>(ctx->trk), ctx->tb);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
@@ -393,13 +393,12 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         CKC(cudaMemcpyAsync(ctx->bsk1, keys->bsk1, n_bsk1 * 4, kind, s));
         if (coeff) { ntt_kernel<F1, false><<<(unsigned)(n_bsk1 / F1::N), ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>(ctx->bsk1, tb, ctx->n1_inv); ++ctx->launches; }
         scale_kernel<F1><<<(unsigned)((n_bsk1 + 255) / 256), 256, 0, s>>>(ctx->bsk1, ctx->bsk1, n_bsk1, make_uint2(c1, h_shoup<u32>(c1, Q1))); ++ctx->launches;
-        const u64 c2 = h_mulmod<u64>(r2, n2i, Q2); const ulonglong2 c2s = make_ulonglong2(c2, h_shoup<u64>(c2, Q2));
         CKC(cudaMemcpyAsync(ctx->bsk2, keys->bsk2, n_bsk2 * 8, kind, s));
         if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_bsk2 / F2::N), ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ctx->bsk2, tb, ctx->n2_inv); ++ctx->launches; }
         key_to_double_kernel<<<(unsigned)((n_bsk2 + 255) / 256), 256, 0, s>>>(ctx->bsk2, reinterpret_cast<double*>(ctx->bsk2), n_bsk2, ctx->n2_inv); ++ctx->launches;
         CKC(cudaMemcpyAsync(ctx->trk, keys->trace, n_trk * 8, kind, s));
         if (coeff) { ntt_kernel<F2, false><<<(unsigned)(n_trk / F2::N), ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ctx->trk, tb, ctx->n2_inv); ++ctx->launches; }
-        scale_kernel<F2><<<(unsigned)((n_trk + 255) / 256), 256, 0, s>>>(ctx->trk, ctx->trk, n_trk, c2s); ++ctx->launches;
+        key_to_double_kernel<<<(unsigned)((n_trk + 255) / 256), 256, 0, s>>>(ctx->trk, reinterpret_cast<double*>(ctx->trk), n_trk, ctx->n2_inv); ++ctx->launches;
         CKC(cudaGetLastError());
         CKC(cudaStreamSynchronize(s));
     }

@@ -373,9 +373,11 @@ keyswitch_kernel(const u32* __restrict__ rlwe, const u32* __restrict__ ksk, u32*
     }
 }
 
-// ---- K4: scale by N^-1, homomorphic trace, forward NTT (integer F2 arithmetic) ----------------------------------------
+// ---- K4: scale by N^-1, homomorphic trace, forward NTT ----------------------------------------------------------------
+// The 11 x 25 digit transforms, the MAC against the trace key and the inverse transforms run on the FP64 pipe like K3
+// (two digits per pass, key words = centred doubles x N^-1); the two final forward transforms (to_ntt_rlwe) stay integer.
 constexpr int TR_THREADS = GeoL2::NT;
-constexpr size_t TR_SMEM = (size_t)2 * F2::N * 8 + (size_t)4 * GeoL2::BUF * 8;
+constexpr size_t TR_SMEM = (size_t)2 * F2::N * 8 + (size_t)2 * GeoL2::BUF * 8;
 
 // sigma_d(p)[pos] as a signed value: source index i0 = pos * d^-1 mod 2N
 __device__ __forceinline__ i64 automorphed(const u64* p, int pos, u32 dinv) {
@@ -384,13 +386,12 @@ __device__ __forceinline__ i64 automorphed(const u64* p, int pos, u32 dinv) {
 }
 
 __global__ void __launch_bounds__(TR_THREADS, 2)
-trace_kernel(u64* __restrict__ ct, const u64* __restrict__ trk, Tables tb) {
-    typedef F2 F; typedef F::Acc Acc; typedef GeoL2 GEO; typedef ArInt<F2> AR;
+trace_kernel(u64* __restrict__ ct, const double* __restrict__ trk, Tables tb) {
+    typedef F2 F; typedef GeoL2 GEO; typedef ArD2 AR;
     constexpr int N = F::N, E = GEO::E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64* acc = reinterpret_cast<u64*>(smem_raw);        // [2][N]: a, b
-    u64* bufs = acc + 2 * N;
-    ExBuf<u64> e0{bufs, bufs + GEO::BUF}, e1{bufs + 2 * GEO::BUF, bufs + 3 * GEO::BUF};
+    u64* acc = reinterpret_cast<u64*>(smem_raw);        // [2][N]: a, b (canonical)
+    double* bx = reinterpret_cast<double*>(acc + 2 * N); double* by = bx + GEO::BUF;
     const int t = threadIdx.x;
     u64* g = ct + (size_t)blockIdx.x * 2 * N;
     for (int e = t; e < 2 * N; e += TR_THREADS) acc[e] = F::csub(F::mul_shoup(g[e], tb.n2_inv), F::Q);   // detector.rs:635-636
@@ -407,28 +408,40 @@ trace_kernel(u64* __restrict__ ct, const u64* __restrict__ trk, Tables tb) {
             if (v < -H) v += (i64)F::Q;
             u[k] = gadget_word<F, GT>(v);
         }
-        Acc ma[E], mb[E];
+        double ma[E], mb[E];
 #pragma unroll
-        for (int k = 0; k < E; ++k) { ma[k] = Acc(); mb[k] = Acc(); }
-        const u64* key = trk + (size_t)step * TR_LEVELS * 2 * N;
+        for (int k = 0; k < E; ++k) { ma[k] = 0.0; mb[k] = 0.0; }
+        const double* key = trk + (size_t)step * TR_LEVELS * 2 * N + out_idx<GEO>(t, 0);
 #pragma unroll 1
-        for (int r = 0; r < TR_LEVELS; ++r) {
-            u64 x[E];
-#pragma unroll
-            for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, GT>(u[k], r);
-            ntt_forward<AR, GEO, LdGlobal>(x, e0, tb.tw2, t, 0);
-            const u64* ka = key + (size_t)r * 2 * N; const u64* kb = ka + N;
+        for (int r = 0; r < TR_LEVELS; r += 2) {
+            const bool pair = r + 1 < TR_LEVELS;                          // 25 digits: 12 pairs and a single
+            double x[E], y[E];
 #pragma unroll
             for (int k = 0; k < E; ++k) {
-                const int idx = out_idx<GEO>(t, k);
-                F::mac(ma[k], x[k], __ldg(ka + idx));
-                F::mac(mb[k], x[k], __ldg(kb + idx));
+                x[k] = D2::from_small(gadget_digit_signed<F, GT>(u[k], r));
+                y[k] = pair ? D2::from_small(gadget_digit_signed<F, GT>(u[k], r + 1)) : 0.0;
+            }
+            ntt_forward2s<AR, GEO, LdGlobal>(x, y, bx, by, tb.tw2d, t, 0);
+            const double* kx = key + (size_t)r * 2 * N;
+            const double* ky = kx + (pair ? 2 * N : 0);                   // (single: y = NTT(0) = 0, any key row)
+#pragma unroll
+            for (int k = 0; k < E; k += 2) {
+                const int o = out_idx<GEO>(0, k) - out_idx<GEO>(0, 0);
+                const double2 xa = ld_stream_f64x2(kx + o), xb = ld_stream_f64x2(kx + N + o);
+                const double2 ya = ld_stream_f64x2(ky + o), yb = ld_stream_f64x2(ky + N + o);
+                ma[k] = __dadd_rn(ma[k], __dadd_rn(D2::mulmod_key(x[k], xa.x), D2::mulmod_key(y[k], ya.x)));
+                ma[k + 1] = __dadd_rn(ma[k + 1], __dadd_rn(D2::mulmod_key(x[k + 1], xa.y), D2::mulmod_key(y[k + 1], ya.y)));
+                mb[k] = __dadd_rn(mb[k], __dadd_rn(D2::mulmod_key(x[k], xb.x), D2::mulmod_key(y[k], yb.x)));
+                mb[k + 1] = __dadd_rn(mb[k + 1], __dadd_rn(D2::mulmod_key(x[k + 1], xb.y), D2::mulmod_key(y[k + 1], yb.y)));
+            }
+            if (r == 8 || r == 18) {                                      // every 10 terms: 0.5q + 10 x 0.66q < 2^53
+#pragma unroll
+                for (int k = 0; k < E; ++k) { ma[k] = D2::renorm(ma[k]); mb[k] = D2::renorm(mb[k]); }
             }
         }
-        u64 ya[E], yb[E];
 #pragma unroll
-        for (int k = 0; k < E; ++k) { ya[k] = F::redc(ma[k]); yb[k] = F::redc(mb[k]); }
-        ntt_inverse2<AR, GEO, LdGlobal>(ya, yb, e0, e1, tb.itw2, t, 0);
+        for (int k = 0; k < E; ++k) { ma[k] = D2::renorm(ma[k]); mb[k] = D2::renorm(mb[k]); }
+        ntt_inverse2s<AR, GEO, LdGlobal>(ma, mb, bx, by, tb.itw2d, t, 0);
         // b' = b + ks.b + sigma_d(b): read the permuted b before anyone overwrites it
         u64 sb[E];
 #pragma unroll
@@ -437,16 +450,18 @@ trace_kernel(u64* __restrict__ ct, const u64* __restrict__ trk, Tables tb) {
 #pragma unroll
         for (int k = 0; k < E; ++k) {
             const int pos = t + GEO::NT * k;
-            acc[pos] = F::add_canon(acc[pos], ya[k]);
-            acc[N + pos] = F::add_canon(F::csub(acc[N + pos] + sb[k], F::Q), yb[k]);
+            i64 va = (i64)acc[pos] + D2::to_i64(ma[k]), vb = (i64)F::csub(acc[N + pos] + sb[k], F::Q) + D2::to_i64(mb[k]);
+            va += va < 0 ? (i64)F::Q : 0; va -= va >= (i64)F::Q ? (i64)F::Q : 0;
+            vb += vb < 0 ? (i64)F::Q : 0; vb -= vb >= (i64)F::Q ? (i64)F::Q : 0;
+            acc[pos] = (u64)va; acc[N + pos] = (u64)vb;
         }
         __syncthreads();
     }
-    // to_ntt_rlwe (detector.rs:638): forward NTT of a and b, canonical output
+    // to_ntt_rlwe (detector.rs:638): forward NTT of a and b, canonical output (integer arithmetic, same two buffers)
     u64 x[E], y[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) { x[k] = acc[t + GEO::NT * k]; y[k] = acc[N + t + GEO::NT * k]; }
-    ntt_forward2<AR, GEO, LdGlobal>(x, y, e0, e1, tb.tw2, t, 0);
+    ntt_forward2s<ArInt<F2>, GEO, LdGlobal>(x, y, reinterpret_cast<u64*>(bx), reinterpret_cast<u64*>(by), tb.tw2, t, 0);
 #pragma unroll
     for (int k = 0; k < E; ++k) { g[out_idx<GEO>(t, k)] = F::canon_lazy(x[k]); g[N + out_idx<GEO>(t, k)] = F::canon_lazy(y[k]); }
 }
