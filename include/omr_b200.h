@@ -123,6 +123,11 @@ int omr_encode_payloads_device(omr_ctx* ctx, const uint64_t* d_pv, const uint16_
  * reduce every word mod q2 in place (inputs < 2^63). */
 int omr_digest_reduce_mod(omr_ctx* ctx, uint64_t* d_words, size_t n_words, void* stream);
 
+/* Streaming detection (README.md:9 "processes incoming messages on-the-fly"): fold the digest of a newly detected batch
+ * into a running digest, acc = (acc + part) mod q2, both canonical.  Packing is a sum over messages, so a running digest
+ * built batch by batch is bit-identical to packing the whole board at once. */
+int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, size_t n_words, void* stream);
+
 /* ---- stage entry points (device pointers) — the stage list of benches/two_level_bs.rs:47-145 ------------------- */
 int omr_l1_blind_rotate_device(omr_ctx* ctx, const uint16_t* d_clue_a, const uint16_t* d_clue_b, size_t B,
                                uint32_t* d_rlwe /*[B][2][1024] sum of the 7 accumulators*/, void* stream);

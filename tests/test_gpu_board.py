@@ -160,3 +160,24 @@ def test_determinism_and_scheduling_independence():
     pick = [0, 592, 1183]
     want = kp.detect(a[pick].cpu().numpy().view(np.uint16), b[pick].cpu().numpy().view(np.uint16), threads=3)
     assert np.array_equal(ref[pick].cpu().numpy().view(np.uint64), want)
+
+
+def test_streaming_running_digest_equals_one_shot(detector, board):
+    """messages arrive in batches; the running digest (omr_digest_add_mod) equals packing the whole board"""
+    import torch
+    import tfhe_omr_b200 as omr
+    _, a, b, payloads = board
+    n = 700
+    rp = omr.RetrievalParams(D, PERT)
+    weights = np.random.default_rng(4).integers(0, 257, (rp.payload_cipher_count * 2, D), dtype=np.uint16)
+    whole = detector.detect((a[:n], b[:n]), index0=100)
+    ref = torch.cat([detector.encode_pertinent_indices(rp, whole, seed=8, n_cipher=5),
+                     detector.encode_pertinent_payloads(whole, payloads[:n], rp.combination_count, 2, weights)])
+    running = torch.zeros_like(ref)
+    for lo, hi in ((0, 1), (1, 300), (300, 700)):
+        pv = detector.detect((a[lo:hi], b[lo:hi]), index0=100 + lo)
+        part = torch.cat([detector.encode_pertinent_indices(rp, pv, seed=8, n_cipher=5),
+                          detector.encode_pertinent_payloads(pv, payloads[lo:hi], rp.combination_count, 2, weights)])
+        detector.digest_accumulate(running, part)
+    torch.cuda.synchronize()
+    assert torch.equal(running, ref)

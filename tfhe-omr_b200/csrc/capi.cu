@@ -538,6 +538,15 @@ int omr_digest_reduce_mod(omr_ctx* ctx, uint64_t* d_words, size_t n, void* strea
     return OMR_OK;
 }
 
+int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, size_t n, void* stream) {
+    if (!ctx || (n && (!d_acc || !d_part))) return OMR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    if (!n) return OMR_OK;
+    digest_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((u64*)d_acc, (const u64*)d_part, n);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
 // ---- host-buffer forms ---------------------------------------------------------------------------------------------------
 int omr_pv_reset(omr_ctx* ctx) {
     if (!ctx) return OMR_ERR_INVALID;

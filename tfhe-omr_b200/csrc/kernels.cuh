@@ -569,6 +569,11 @@ __global__ void reduce_partials_kernel(const u64* __restrict__ partial, int n_ch
     for (int c = 0; c < n_chunks; ++c) { s += p[(size_t)c * 2 * F2::N]; if ((c & 4095) == 4095) s = F2::canon_lazy(s); }
     out[(size_t)cipher * 2 * F2::N + e] = F2::canon_lazy(s);
 }
+// streaming: running digest += digest of the newly detected messages (mod q2); both canonical
+__global__ void digest_add_kernel(u64* acc, const u64* __restrict__ part, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] = F2::csub(acc[i] + part[i], F2::Q);
+}
 __global__ void digest_mod_kernel(u64* words, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) words[i] = F2::canon_lazy(words[i]);

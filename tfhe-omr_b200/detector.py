@@ -213,6 +213,13 @@ class Detector:
         self._ck(self.L.omr_digest_reduce_mod(self.h, digest.data_ptr(), digest.numel(), self._stream()))
         return digest
 
+    def digest_accumulate(self, running, part):
+        """streaming: running = (running + part) mod q2 (both canonical int64 CUDA tensors of the same shape)"""
+        if running.shape != part.shape:
+            raise OmrError(_lib.OMR_ERR_INVALID, "digest shapes differ")
+        self._ck(self.L.omr_digest_add_mod(self.h, running.data_ptr(), part.data_ptr(), running.numel(), self._stream()))
+        return running
+
     # -- host-buffer ("e2e") path: what the Rust shim binds ------------------------------------------------------------
     def pv_reset(self):
         self._ck(self.L.omr_pv_reset(self.h))
