@@ -10,6 +10,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    # a fresh checkout has no built artefacts (*.so are git-ignored): build them once (nvcc cross-compiles without a GPU)
+    lib = os.path.join(ROOT, "tfhe-omr_b200", "lib", "libomr_b200.so")
+    orc = os.path.join(ROOT, "oracle", "libomr_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")

@@ -194,24 +194,29 @@ int detect_device(omr_ctx* ctx, const unsigned short* d_ca, const unsigned short
     if (times) *times = omr_stage_times{};
     if (!B) return OMR_OK;
     const size_t C = ctx->chunk;
-    if (!ctx->overlap || B <= C) {                                 // small batch: plain sequence on the caller's stream
-        if ((st = ensure_scratch(ctx, B))) return st;
-        if (times) CK(cudaEventRecord(ctx->ev[0], s));
-        if ((st = launch_l1(ctx, d_ca, d_cb, B, ctx->s_rlwe1, s))) return st;
-        if ((st = launch_ks(ctx, ctx->s_rlwe1, B, ctx->s_lwe2, s))) return st;
-        if (times) CK(cudaEventRecord(ctx->ev[1], s));
-        if ((st = launch_l2(ctx, ctx->s_lwe2, B, d_pv, s))) return st;
-        if (times) CK(cudaEventRecord(ctx->ev[2], s));
-        if ((st = launch_trace(ctx, d_pv, B, s))) return st;
-        if (times) {
-            CK(cudaEventRecord(ctx->ev[3], s));
-            CK(cudaEventSynchronize(ctx->ev[3]));
-            float a = 0, b = 0, c = 0;
-            CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
-            CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
-            CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
-            times->first_level_bootstrapping_ms = a; times->second_level_bootstrapping_ms = b; times->trace_ms = c;
-            times->detect_ms = a + b + c;
+    if (!ctx->overlap || B <= C) {                                 // plain sequence on the caller's stream, scratch bounded by MAXB
+        const size_t MAXB = 16384;
+        if ((st = ensure_scratch(ctx, B < MAXB ? B : MAXB))) return st;
+        for (size_t off = 0; off < B; off += MAXB) {
+            const size_t nb = B - off < MAXB ? B - off : MAXB;
+            u64* pv = d_pv + off * OMR_PV_WORDS;
+            if (times) CK(cudaEventRecord(ctx->ev[0], s));
+            if ((st = launch_l1(ctx, d_ca + off * CLUE_N, d_cb + off * CLUE_COUNT, nb, ctx->s_rlwe1, s))) return st;
+            if ((st = launch_ks(ctx, ctx->s_rlwe1, nb, ctx->s_lwe2, s))) return st;
+            if (times) CK(cudaEventRecord(ctx->ev[1], s));
+            if ((st = launch_l2(ctx, ctx->s_lwe2, nb, pv, s))) return st;
+            if (times) CK(cudaEventRecord(ctx->ev[2], s));
+            if ((st = launch_trace(ctx, pv, nb, s))) return st;
+            if (times) {
+                CK(cudaEventRecord(ctx->ev[3], s));
+                CK(cudaEventSynchronize(ctx->ev[3]));
+                float a = 0, b = 0, c = 0;
+                CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+                CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+                CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
+                times->first_level_bootstrapping_ms += a; times->second_level_bootstrapping_ms += b; times->trace_ms += c;
+                times->detect_ms += a + b + c;
+            }
         }
         return OMR_OK;
     }
