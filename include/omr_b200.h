@@ -128,6 +128,14 @@ int omr_digest_reduce_mod(omr_ctx* ctx, uint64_t* d_words, size_t n_words, void*
  * built batch by batch is bit-identical to packing the whole board at once. */
 int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, size_t n_words, void* stream);
 
+/* Recipient side (Retriever::decode_pertinent_indices / decode_combined_payloads, retriever.rs:63-130,
+ * 318-362): decrypt n NTT-domain RLWE ciphertexts with the recipient's NTT-domain secret z2 (b - a*z2, inverse NTT) and
+ * decode every coefficient c to round_half_up(c * 257 / q2) folded into [0,257) — exact integer rounding instead of the
+ * reference's BigDecimal.  d_out [n][2048] u16.  The bucket scan and the mod-257 solver run on the host
+ * (tfhe_omr_b200.retriever). */
+int omr_decrypt_decode_device(omr_ctx* ctx, const uint64_t* d_z2_ntt /*[2048]*/, const uint64_t* d_ct /*[n][2][2048]*/, size_t n,
+                              uint16_t* d_out /*[n][2048]*/, void* stream);
+
 /* ---- stage entry points (device pointers) — the stage list of benches/two_level_bs.rs:47-145 ------------------- */
 int omr_l1_blind_rotate_device(omr_ctx* ctx, const uint16_t* d_clue_a, const uint16_t* d_clue_b, size_t B,
                                uint32_t* d_rlwe /*[B][2][1024] sum of the 7 accumulators*/, void* stream);

@@ -47,6 +47,15 @@ def test_full_board_detect_pack_decode(detector, keypack, board):
     assert list(found) == list(planted)                                        # retrieved set == planted set
     for i, p in zip(found, solved):
         assert np.array_equal(p, payloads[i])                                  # payloads recovered exactly
+    # the product's own recipient side (GPU decrypt/decode + host solver) agrees with the oracle's Retriever
+    s0, z1, s2, z2 = keypack.secrets()
+    z2n = np.where(z2 < 0, O.Q2 + z2.astype(np.int64), z2.astype(np.int64)).astype(np.uint64)
+    O.lib().orc_ntt2_forward(O.ptr(z2n), 1)
+    ret = omr.Retriever(detector, rp, z2n)
+    slots = detector.decrypt_decode(ret.key, idx).cpu().numpy().view(np.uint16)
+    assert np.array_equal(slots[0], keypack.decrypt_decode(idx[0].cpu().numpy().view(np.uint64)).astype(np.uint16))
+    found2, solved2 = ret.decode_digest(idx, pay, weights)
+    assert found2 == list(planted) and np.array_equal(solved2, solved)
     # bit-exact against the oracle on a sample: 4 pertinent + 4 random messages
     sample = np.concatenate([planted[:4], np.array([0, 1, 31337, D - 1])])
     ref = keypack.detect(a[sample], b[sample], threads=8)

@@ -552,6 +552,22 @@ int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, si
     return OMR_OK;
 }
 
+int omr_decrypt_decode_device(omr_ctx* ctx, const uint64_t* d_z2_ntt, const uint64_t* d_ct, size_t n, uint16_t* d_out, void* stream) {
+    if (!ctx || (n && (!d_z2_ntt || !d_ct || !d_out))) { ctx_fail(ctx, "decrypt_decode: null argument"); return OMR_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    if (!n) return OMR_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int st; if ((st = ensure_partial(ctx, n * F2::N))) return st;
+    const size_t total = n * F2::N;
+    decrypt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const u64*)d_ct, (const u64*)d_z2_ntt, ctx->s_partial, n);
+    ++ctx->launches; CK(cudaGetLastError());
+    ntt_kernel<F2, true><<<(unsigned)n, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ctx->s_partial, ctx->tb, ctx->n2_inv);
+    ++ctx->launches; CK(cudaGetLastError());
+    decode_round_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ctx->s_partial, d_out, total);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
 // ---- host-buffer forms ---------------------------------------------------------------------------------------------------
 int omr_pv_reset(omr_ctx* ctx) {
     if (!ctx) return OMR_ERR_INVALID;

@@ -579,6 +579,25 @@ __global__ void digest_mod_kernel(u64* words, size_t n) {
     if (i < n) words[i] = F2::canon_lazy(words[i]);
 }
 
+// ---- recipient side: decrypt + decode a batch of NTT-domain RLWE ciphertexts -----------------------------
+// d = b - a (.) z2 (retriever.rs:79,339: sub_mul), then after the inverse NTT every coefficient c is decoded as
+// t = round_half_up(c * p / q2), t >= p -> t - p (retriever.rs:84-89, 349-355) in exact integer arithmetic.
+__global__ void decrypt_kernel(const u64* __restrict__ ct /*[n][2][N]*/, const u64* __restrict__ z_ntt /*[N]*/, u64* __restrict__ out /*[n][N]*/, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * F2::N) return;
+    const size_t m = i / F2::N, k = i % F2::N;
+    const u64 a = ct[m * 2 * F2::N + k], b = ct[m * 2 * F2::N + F2::N + k];
+    const u64 az = (u64)(((u128)a * z_ntt[k]) % Q2);
+    out[i] = b >= az ? b - az : b + Q2 - az;
+}
+__global__ void decode_round_kernel(const u64* __restrict__ in /*[n][N] canonical*/, unsigned short* __restrict__ out, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    u64 t = (2ull * OUT_P * in[i] + Q2) / (2ull * Q2);        // 514 * c < 2^60: no overflow
+    if (t >= OUT_P) t -= OUT_P;
+    out[i] = (unsigned short)t;
+}
+
 // ---- standalone batched NTTs (key upload in coefficient form, tests, API completeness) -----------------------------
 template <class F> struct GeoOf;
 template <> struct GeoOf<F1> { typedef GeoL1 G; };

@@ -220,6 +220,13 @@ class Detector:
         self._ck(self.L.omr_digest_add_mod(self.h, running.data_ptr(), part.data_ptr(), running.numel(), self._stream()))
         return running
 
+    def decrypt_decode(self, z2_ntt, cts):
+        """recipient side: decoded slots (values mod 257) of NTT-domain RLWE ciphertexts, int16 CUDA tensor [n][2048]"""
+        torch = _torch()
+        out = torch.empty((cts.shape[0], N2), dtype=torch.int16, device=cts.device)
+        self._ck(self.L.omr_decrypt_decode_device(self.h, z2_ntt.data_ptr(), cts.data_ptr(), cts.shape[0], out.data_ptr(), self._stream()))
+        return out
+
     # -- host-buffer ("e2e") path: what the Rust shim binds ------------------------------------------------------------
     def pv_reset(self):
         self._ck(self.L.omr_pv_reset(self.h))
