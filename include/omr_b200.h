@@ -136,6 +136,13 @@ int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, si
 int omr_decrypt_decode_device(omr_ctx* ctx, const uint64_t* d_z2_ntt /*[2048]*/, const uint64_t* d_ct /*[n][2][2048]*/, size_t n,
                               uint16_t* d_out /*[n][2048]*/, void* stream);
 
+/* Sender side (Sender::gen_clues -> ClueKey::gen_clues, sender.rs:27-30, key_gen/clue.rs:27-34): `count` clues
+ * under the clue public key (pa, pb) [512] u16 each, for global message indices index0.., encrypting d_msgs[i][7] (values
+ * mod 8; NULL = seven 0's as the reference does).  Randomness is a counter hash of (seed, message index), see DESIGN.md.
+ * d_a [count][512], d_b [count][7]. */
+int omr_gen_clues_device(omr_ctx* ctx, const uint16_t* d_pa, const uint16_t* d_pb, uint64_t seed, uint64_t index0, size_t count,
+                         const uint8_t* d_msgs, uint16_t* d_a, uint16_t* d_b, void* stream);
+
 /* ---- stage entry points (device pointers) — the stage list of benches/two_level_bs.rs:47-145 ------------------- */
 int omr_l1_blind_rotate_device(omr_ctx* ctx, const uint16_t* d_clue_a, const uint16_t* d_clue_b, size_t B,
                                uint32_t* d_rlwe /*[B][2][1024] sum of the 7 accumulators*/, void* stream);

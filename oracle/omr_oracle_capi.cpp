@@ -106,6 +106,15 @@ void orc_gen_clues(void* hh, uint64_t seed, uint64_t index0, size_t count, uint1
     auto* h = (OrcHandle*)hh;
     parallel_for((size_t)count, threads, [&](size_t i) { gen_clue(h->ck, seed, index0 + i, nullptr, a + i * CLUE_N, b + i * CLUE_COUNT); });
 }
+// counter-based variant (bit-exact twin of the CUDA clue_gen_kernel)
+void orc_gen_clues_cb(void* hh, uint64_t seed, uint64_t index0, size_t count, const uint8_t* msgs /*nullable [count][7]*/, uint16_t* a, uint16_t* b, int threads) {
+    auto* h = (OrcHandle*)hh;
+    parallel_for((size_t)count, threads, [&](size_t i) { gen_clue_cb(h->ck, seed, index0 + i, msgs ? msgs + i * CLUE_COUNT : nullptr, a + i * CLUE_N, b + i * CLUE_COUNT); });
+}
+void orc_clue_key(void* hh, uint16_t* pa, uint16_t* pb) {
+    auto* h = (OrcHandle*)hh;
+    std::memcpy(pa, h->ck.pa.data(), CLUE_N * 2); std::memcpy(pb, h->ck.pb.data(), CLUE_N * 2);
+}
 void orc_gen_clue_msgs(void* hh, uint64_t seed, uint64_t index, const uint32_t* msgs, uint16_t* a, uint16_t* b) {
     gen_clue(((OrcHandle*)hh)->ck, seed, index, msgs, a, b);
 }

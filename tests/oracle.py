@@ -56,6 +56,8 @@ def lib(native=False):
     L.orc_secret.argtypes = [vp, vp, vp, vp, vp]
     L.orc_gen_clues.argtypes = [vp, u64, u64, sz, vp, vp, i32]
     L.orc_gen_clue_msgs.argtypes = [vp, u64, u64, vp, vp, vp]
+    L.orc_gen_clues_cb.argtypes = [vp, u64, u64, sz, vp, vp, vp, i32]
+    L.orc_clue_key.argtypes = [vp, vp, vp]
     L.orc_decrypt_clue.argtypes = [vp, vp, vp, vp]
     L.orc_detect.argtypes = [vp, vp, vp, sz, vp, i32]
     L.orc_l1.argtypes = [vp, vp, vp, sz, vp, i32]
@@ -144,6 +146,17 @@ class KeyPack:
         a = np.zeros((count, CLUE_N), np.uint16); b = np.zeros((count, CLUE_COUNT), np.uint16)
         self.L.orc_gen_clues(self.h, seed, index0, count, ptr(a), ptr(b), threads)
         return a, b
+
+    def gen_clues_cb(self, seed, count, index0=0, msgs=None, threads=8):
+        """counter-based clue generation (bit-exact twin of the CUDA clue_gen_kernel)"""
+        a = np.zeros((count, CLUE_N), np.uint16); b = np.zeros((count, CLUE_COUNT), np.uint16)
+        m = None if msgs is None else np.ascontiguousarray(msgs, np.uint8).reshape(count, CLUE_COUNT)
+        self.L.orc_gen_clues_cb(self.h, seed, index0, count, None if m is None else ptr(m), ptr(a), ptr(b), threads)
+        return a, b
+
+    def clue_key(self):
+        pa = np.zeros(CLUE_N, np.uint16); pb = np.zeros(CLUE_N, np.uint16)
+        self.L.orc_clue_key(self.h, ptr(pa), ptr(pb)); return pa, pb
 
     def gen_clue_msgs(self, seed, index, msgs):
         m = np.asarray(msgs, np.uint32); a = np.zeros(CLUE_N, np.uint16); b = np.zeros(CLUE_COUNT, np.uint16)

@@ -190,3 +190,24 @@ def test_streaming_running_digest_equals_one_shot(detector, board):
         detector.digest_accumulate(running, part)
     torch.cuda.synchronize()
     assert torch.equal(running, ref)
+
+
+def test_gpu_clue_generation_matches_oracle_and_is_detected(detector, keypack, decoy):
+    """batched clue generation on the GPU — bit-exact with the oracle's counter-based twin, decrypts to the
+    planted plaintexts, and clues of seven 0's made on the GPU are detected as pertinent."""
+    import torch
+    pa, pb = keypack.clue_key()
+    n = 300
+    msgs = np.random.default_rng(2).integers(0, 8, (n, 7), dtype=np.uint8)
+    a, b = detector.gen_clues((pa, pb), n, seed=0xABC, index0=1000, msgs=msgs)
+    ra, rb = keypack.gen_clues_cb(0xABC, n, index0=1000, msgs=msgs)
+    ah, bh = a.cpu().numpy().view(np.uint16), b.cpu().numpy().view(np.uint16)
+    assert np.array_equal(ah, ra) and np.array_equal(bh, rb)
+    for i in (0, 7, n - 1):
+        assert np.array_equal(keypack.decrypt_clue(ah[i], bh[i]), msgs[i])
+    z, zb = detector.gen_clues((pa, pb), 3, seed=5)                       # the reference's clue: seven 0's (clue.rs:32)
+    dpa, dpb = decoy.clue_key()
+    o, ob = detector.gen_clues((dpa, dpb), 3, seed=6)                     # someone else's clues
+    pv = detector.detect((torch.cat([z, o]), torch.cat([zb, ob]))).to_host()
+    dec = [keypack.decrypt_decode(pv[i]) for i in range(6)]
+    assert all(d[0] == 1 and not d[1:].any() for d in dec[:3]) and all(not d.any() for d in dec[3:])

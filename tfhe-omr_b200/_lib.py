@@ -15,7 +15,7 @@ EXPORTS = [
     "omr_retrieval_params_init", "omr_detect_batch", "omr_pv_reset", "omr_encode_indices", "omr_encode_payloads",
     "omr_detect_batch_device", "omr_encode_indices_device", "omr_encode_payloads_device", "omr_digest_reduce_mod",
     "omr_l1_blind_rotate_device", "omr_keyswitch_device", "omr_l2_blind_rotate_device", "omr_trace_device",
-    "omr_ntt_forward_device", "omr_ntt_inverse_device", "omr_launch_count", "omr_mulmod_peak", "omr_digest_add_mod", "omr_decrypt_decode_device",
+    "omr_ntt_forward_device", "omr_ntt_inverse_device", "omr_launch_count", "omr_mulmod_peak", "omr_digest_add_mod", "omr_decrypt_decode_device", "omr_gen_clues_device",
 ]
 
 
@@ -73,6 +73,7 @@ def load():
     L.omr_ntt_inverse_device.restype = i32; L.omr_ntt_inverse_device.argtypes = [vp, i32, vp, sz, vp]
     L.omr_digest_add_mod.restype = i32; L.omr_digest_add_mod.argtypes = [vp, vp, vp, sz, vp]
     L.omr_decrypt_decode_device.restype = i32; L.omr_decrypt_decode_device.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.omr_gen_clues_device.restype = i32; L.omr_gen_clues_device.argtypes = [vp, vp, vp, u64, u64, sz, vp, vp, vp, vp]
     L.omr_mulmod_peak.restype = i32; L.omr_mulmod_peak.argtypes = [vp, i32, i32, P(C.c_double)]
     _lib = L
     return L

@@ -568,6 +568,16 @@ int omr_decrypt_decode_device(omr_ctx* ctx, const uint64_t* d_z2_ntt, const uint
     return OMR_OK;
 }
 
+int omr_gen_clues_device(omr_ctx* ctx, const uint16_t* d_pa, const uint16_t* d_pb, uint64_t seed, uint64_t index0, size_t count,
+                         const uint8_t* d_msgs, uint16_t* d_a, uint16_t* d_b, void* stream) {
+    if (!ctx || (count && (!d_pa || !d_pb || !d_a || !d_b))) { ctx_fail(ctx, "gen_clues: null argument"); return OMR_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    if (!count) return OMR_OK;
+    clue_gen_kernel<<<(unsigned)count, CLUE_THREADS, 0, (cudaStream_t)stream>>>(d_pa, d_pb, seed, index0, d_msgs, d_a, d_b);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
 // ---- host-buffer forms ---------------------------------------------------------------------------------------------------
 int omr_pv_reset(omr_ctx* ctx) {
     if (!ctx) return OMR_ERR_INVALID;

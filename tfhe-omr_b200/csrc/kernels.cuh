@@ -598,6 +598,50 @@ __global__ void decode_round_kernel(const u64* __restrict__ in /*[n][N] canonica
     out[i] = (unsigned short)t;
 }
 
+// ---- sender side: batched clue generation -------------------------------------------------------------------
+// ClueKey::gen_clues (key_gen/clue.rs:27-34 -> [UPSTREAM] LwePublicKeyRlweMode::encrypt_multi_messages): with the
+// public key (pa, pb = pa*s0 + e) over Z_2048[X]/(X^512+1): clue = (pa*r + e1, first 7 coefficients of pb*r + e2 + 256*m),
+// r binary.  One CTA per clue; every random draw is a counter hash of (seed, message index, domain, position) and the
+// rounded Gaussian comes from an integer cumulative table — bit-identical to the oracle's gen_clue_cb.
+__constant__ u32 CLUE_CDT[5] = {1947496405u, 3992218608u, 4283915214u, 4294862567u, 4294967049u};   // P(|e| <= k) 2^32, sigma 0.8293
+__device__ __forceinline__ u64 clue_hash(u64 seed, u64 index, u32 domain, u32 pos) {
+    return mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (index + 1)) ^ ((((u64)domain << 32) | pos) * 0xD1342543DE82EF95ull));
+}
+__device__ __forceinline__ int clue_gauss(u64 h) {
+    const u32 u = (u32)h; int m = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) m += u >= CLUE_CDT[k];
+    return (h >> 63) ? -m : m;
+}
+constexpr int CLUE_THREADS = 256;
+__global__ void __launch_bounds__(CLUE_THREADS)
+clue_gen_kernel(const unsigned short* __restrict__ pa, const unsigned short* __restrict__ pb, u64 seed, u64 index0,
+                const unsigned char* __restrict__ msgs /*nullable [count][7]*/, unsigned short* __restrict__ out_a, unsigned short* __restrict__ out_b) {
+    __shared__ unsigned short s_pa[CLUE_N], s_pb[CLUE_N];
+    __shared__ unsigned char s_r[CLUE_N];
+    const u64 index = index0 + blockIdx.x;
+    for (int j = threadIdx.x; j < CLUE_N; j += CLUE_THREADS) {
+        s_pa[j] = pa[j]; s_pb[j] = pb[j];
+        s_r[j] = (unsigned char)(clue_hash(seed, index, 0, (u32)j) & 1);
+    }
+    __syncthreads();
+    // (p * r)[i] = SUM_{j<=i} p[i-j] r[j] - SUM_{j>i} p[512+i-j] r[j]   (negacyclic, mod 2048 by wrap-around of int32)
+    for (int i = threadIdx.x; i < CLUE_N; i += CLUE_THREADS) {
+        int acc = 0;
+        for (int j = 0; j <= i; ++j) acc += s_r[j] ? (int)s_pa[i - j] : 0;
+        for (int j = i + 1; j < CLUE_N; ++j) acc -= s_r[j] ? (int)s_pa[CLUE_N + i - j] : 0;
+        out_a[(size_t)blockIdx.x * CLUE_N + i] = (unsigned short)((acc + clue_gauss(clue_hash(seed, index, 1, (u32)i))) & (CLUE_Q - 1));
+    }
+    if (threadIdx.x < CLUE_COUNT) {
+        const int c = threadIdx.x;
+        int acc = 0;
+        for (int j = 0; j <= c; ++j) acc += s_r[j] ? (int)s_pb[c - j] : 0;
+        for (int j = c + 1; j < CLUE_N; ++j) acc -= s_r[j] ? (int)s_pb[CLUE_N + c - j] : 0;
+        const int m = msgs ? (int)(msgs[(size_t)blockIdx.x * CLUE_COUNT + c] & 7) * (CLUE_Q / 8) : 0;
+        out_b[(size_t)blockIdx.x * CLUE_COUNT + c] = (unsigned short)((acc + clue_gauss(clue_hash(seed, index, 2, (u32)c)) + m) & (CLUE_Q - 1));
+    }
+}
+
 // ---- standalone batched NTTs (key upload in coefficient form, tests, API completeness) -----------------------------
 template <class F> struct GeoOf;
 template <> struct GeoOf<F1> { typedef GeoL1 G; };

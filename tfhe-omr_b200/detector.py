@@ -227,6 +227,22 @@ class Detector:
         self._ck(self.L.omr_decrypt_decode_device(self.h, z2_ntt.data_ptr(), cts.data_ptr(), cts.shape[0], out.data_ptr(), self._stream()))
         return out
 
+    def gen_clues(self, clue_key, count, seed, index0=0, msgs=None):
+        """sender side (Sender::gen_clues, sender.rs:27-30) batched on the GPU: clue_key = (pa, pb) u16[512] each.
+        Returns CUDA int16 tensors (a [count][512], b [count][7])."""
+        torch = _torch()
+        dev = f"cuda:{self.device}"
+        pa, pb = (torch.from_numpy(np.ascontiguousarray(k, np.uint16).view(np.int16)).to(dev) if not hasattr(k, "data_ptr") else k for k in clue_key)
+        if pa.numel() != CLUE_N or pb.numel() != CLUE_N:
+            raise OmrError(_lib.OMR_ERR_INVALID, "clue key must be two polynomials of 512 coefficients")
+        a = torch.empty((count, CLUE_N), dtype=torch.int16, device=dev); b = torch.empty((count, CLUE_COUNT), dtype=torch.int16, device=dev)
+        dm = None
+        if msgs is not None:
+            dm = torch.from_numpy(np.ascontiguousarray(msgs, np.uint8).reshape(count, CLUE_COUNT)).to(dev)
+        self._ck(self.L.omr_gen_clues_device(self.h, pa.data_ptr(), pb.data_ptr(), seed, index0, count,
+                                             dm.data_ptr() if dm is not None else None, a.data_ptr(), b.data_ptr(), self._stream()))
+        return a, b
+
     # -- host-buffer ("e2e") path: what the Rust shim binds ------------------------------------------------------------
     def pv_reset(self):
         self._ck(self.L.omr_pv_reset(self.h))
