@@ -162,8 +162,8 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
     ExBuf<u32> eb{acc + 2 * N, acc + 2 * N + GEO::BUF};
     if (threadIdx.x == 0) mbar_init(mbar, 1);
     for (int i = threadIdx.x; i < N; i += THREADS) { s_tw[i] = tb.tw1[i]; if (!HALF) s_itw_smem[i] = tb.itw1[i]; }
-    for (int i = t; i < CLUE_N; i += L1_GROUP) ca[i] = clue_a[(size_t)msg * CLUE_N + i];
-    init_acc<F, GEO>(acc, tb.lut1, clue_b[(size_t)msg * CLUE_COUNT + c], t);
+    for (int i = t; i < CLUE_N; i += L1_GROUP) ca[i] = clue_a[(size_t)msg * CLUE_N + i] & (CLUE_Q - 1);   // canonical mod 2048
+    init_acc<F, GEO>(acc, tb.lut1, clue_b[(size_t)msg * CLUE_COUNT + c] & (CLUE_Q - 1), t);
     __syncthreads();
     if (threadIdx.x == 0) tma_load(ktile, bsk1, CFG::TILE_WORDS * 4, mbar);
     const int bar = 1 + slot;
@@ -260,7 +260,7 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
     unsigned short* la = reinterpret_cast<unsigned short*>(s_tw + N);   // of shared memory is too small to hold them
     const int msg = blockIdx.x, t = threadIdx.x;
     for (int i = t; i < N; i += L2_THREADS) s_tw[i] = tb.tw2d[i];
-    for (int i = t; i < LWE2_STRIDE_IN; i += L2_THREADS) la[i] = (unsigned short)lwe[(size_t)msg * LWE2_STRIDE_IN + i];
+    for (int i = t; i < LWE2_STRIDE_IN; i += L2_THREADS) la[i] = (unsigned short)(lwe[(size_t)msg * LWE2_STRIDE_IN + i] & (LWE2_Q - 1));
     __syncthreads();
     init_acc<F, GEO>(acc, tb.lut2, la[LWE2_N], t);
     __syncthreads();
