@@ -370,6 +370,16 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         for (u32 x = 1; x < M; x += 2) if ((x * d) % M == 1) { inv = x; break; }
         tb.trace_dinv[t] = inv;
     }
+    {   // first-pass twiddles (uniform across threads) into constant memory of this device
+        uint2 h1[16] = {}; double2 h2[8] = {};
+        for (int i = 1; i < 16; ++i) h1[i] = tw1[i];
+        for (int i = 1; i < 8; ++i) {
+            const u64 v = tw2[i].x; const double c = v > (Q2 >> 1) ? -(double)(int64_t)(Q2 - v) : (double)(int64_t)v;
+            h2[i] = make_double2(c, (double)((long double)c / (long double)Q2));
+        }
+        CKC(cudaMemcpyToSymbol(c_tw1_head, h1, sizeof h1));
+        CKC(cudaMemcpyToSymbol(c_tw2d_head, h2, sizeof h2));
+    }
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<8, false>::SMEM));
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1_HALF_EXCLUSIVE_SMEM));
     ctx->l1_half = getenv("OMR_L1_HALF") != nullptr;

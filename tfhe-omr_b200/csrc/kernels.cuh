@@ -189,7 +189,7 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
                 u32 x[E];
 #pragma unroll
                 for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, G>(u[k], r);
-                ntt_forward<AR, GEO, LdShared>(x, eb, s_tw, t, bar);
+                ntt_forward<AR, GEO, LdSharedC>(x, eb, s_tw, t, bar);
                 if (r == 0 && (p == 0 || HALF)) { mbar_wait(mbar, phase & 1); ++phase; }   // the (half) tile has landed
                 const u32* ka = ktile + (size_t)((HALF ? 0 : p * L) + r) * 2 * N + out_idx<GEO>(t, 0);
                 const u32* kb = ka + N;
@@ -284,7 +284,7 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
                     x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r));
                     y[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r + 1));
                 }
-                ntt_forward2s<AR, GEO, LdShared>(x, y, bx, by, s_tw, t, 0);
+                ntt_forward2s<AR, GEO, LdSharedC>(x, y, bx, by, s_tw, t, 0);
                 const double* kx = key + (size_t)(p * L + r) * 2 * N;         // rows r and r+1: [a | b] each
 #pragma unroll
                 for (int k = 0; k < E; k += 2) {

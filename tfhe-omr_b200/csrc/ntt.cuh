@@ -126,8 +126,20 @@ struct ArD2 {
         a = D2::renorm(__dadd_rn(u, v)); b = D2::mulmod(__dadd_rn(u, -v), w.x, w.y);
     }
 };
-struct LdGlobal { template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return __ldg(p); } };
-struct LdShared { template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
+// The twiddles of the first pass are the same for every thread (block index 0): they live in constant memory and reach
+// the multiplier as constant-bank operands — no load instruction, no register.  Filled at context creation.
+__constant__ uint2 c_tw1_head[16];       // level 1 forward, indices 1..15 (stages 0-3)
+__constant__ double2 c_tw2d_head[8];     // level 2 forward (FP64 form), indices 1..7 (stages 0-2)
+template <class TW> __device__ __forceinline__ const TW* const_head();
+template <> __device__ __forceinline__ const uint2* const_head<uint2>() { return c_tw1_head; }
+template <> __device__ __forceinline__ const double2* const_head<double2>() { return c_tw2d_head; }
+template <class TW> struct HasConstHead { static constexpr bool value = false; };
+template <> struct HasConstHead<uint2> { static constexpr bool value = true; };
+template <> struct HasConstHead<double2> { static constexpr bool value = true; };
+
+struct LdGlobal { static constexpr bool USE_CONST_HEAD = false; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return __ldg(p); } };
+struct LdShared { static constexpr bool USE_CONST_HEAD = false; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
+struct LdSharedC { static constexpr bool USE_CONST_HEAD = true; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
 
 template <class AR, class GEO, int P, class LD>
 __device__ __forceinline__ void fwd_pass(typename AR::T (&x)[GEO::E], const typename AR::TW* __restrict__ tw, int t) {
@@ -141,7 +153,9 @@ __device__ __forceinline__ void fwd_pass(typename AR::T (&x)[GEO::E], const type
             const int half = PS::EP >> (l + 1);
 #pragma unroll
             for (int sb = 0; sb < (1 << l); ++sb) {
-                const typename AR::TW w = LD::ld(&tw[(1 << (PS::S0 + l)) + (j << l) + sb]);
+                typename AR::TW w;
+                if constexpr (P == 0 && HasConstHead<typename AR::TW>::value && LD::USE_CONST_HEAD) w = const_head<typename AR::TW>()[(1 << l) + sb];
+                else w = LD::ld(&tw[(1 << (PS::S0 + l)) + (j << l) + sb]);
 #pragma unroll
                 for (int h = 0; h < half; ++h) {
                     const int lo = g * PS::EP + sb * 2 * half + h, hi = lo + half;
