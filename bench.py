@@ -320,20 +320,33 @@ def run_reference(args):
     kp = O.KeyPack(blobs=O.random_key_blobs(20261018), native=native)
     rng = np.random.default_rng(3)
     a = rng.integers(0, 2048, (sample, 512), dtype=np.uint16); b = rng.integers(0, 2048, (sample, 7), dtype=np.uint16)
+    payloads = rng.integers(0, 256, (sample, 612), dtype=np.uint16)
+    rp = O.retrieval_params(D_BOARD, PERTINENT)
+    n_idx, n_pay = rp["max_encode_indices_cipher_count"], rp["payload_cipher_count"]
+    weights = rng.integers(0, 257, (n_pay * 2, D_BOARD), dtype=np.uint16)
+
+    def step():                                          # the same hot path: detect -> index digest -> payload digest
+        pv = kp.detect(a, b, threads=cores)
+        for c in range(n_idx):
+            O.encode_indices(D_BOARD, PERTINENT, pv, 0, 0xC0FFEE, c)
+        O.encode_payloads(pv, payloads, 0, weights, n_pay, threads=cores)
+
     for _ in range(min(args.warmup, 1)):
-        kp.detect(a[:cores], b[:cores], threads=cores)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        kp.detect(a, b, threads=cores)
+        step()
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    desc = (f"oracle detect (C++ port, {'-march=native' if native else 'portable'}) on {sample} messages per step, {cores} threads "
+    desc = (f"oracle port of detect + both packers (C++, {'-march=native' if native else 'portable'}) on {sample} messages per step, {cores} threads "
             f"(one message per thread, examples/omr.rs:160-164)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "messages/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": round(value / README_SINGLE_CORE_MSGS, 3), "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "omr --payload-count 65536 (BASELINE.json configs[3]): detect", "D": D_BOARD, "messages_per_step": sample},
+        "config": {"workload": "omr --payload-count 65536 (BASELINE.json configs[3]): detect + index/payload digest", "D": D_BOARD,
+                   "messages_per_step_per_gpu": sample, "pertinent": PERTINENT, "index_ciphertexts": n_idx, "payload_ciphertexts": n_pay,
+                   "parallelism": f"{cores} host threads, one message per thread"},
         "cpu_baseline": {"value": round(value, 3), "unit": "messages/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": round(value, 3), "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

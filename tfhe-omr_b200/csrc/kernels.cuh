@@ -350,14 +350,25 @@ keyswitch_kernel(const u32* __restrict__ rlwe, const u32* __restrict__ ksk, u32*
 #pragma unroll
         for (int m = 0; m < KS_MB; ++m) w[m] = uw[m][i];
         const u32* row = ksk + (size_t)i * KS_LEVELS * KSK_PAD + col;
-#pragma unroll 9
-        for (int j = 0; j < KS_LEVELS; ++j) {
-            const i32 k = (i32)__ldg(row + (size_t)j * KSK_PAD);
+        // 32-bit partial sums over halves of the 27 levels (14 x 2^27 < 2^31), widened once per half: IMAD instead of
+        // IMAD.WIDE (64 vs 25 lanes/clk/SM) in the innermost loop
 #pragma unroll
-            for (int m = 0; m < KS_MB; ++m) {
-                const i32 d = j < KS_LEVELS - 1 ? ((w[m] >> j) & 1) - 1 : (w[m] >> (KS_LEVELS - 1));
-                acc[m] += (i64)d * k;
+        for (int half = 0; half < 2; ++half) {
+            i32 part[KS_MB];
+#pragma unroll
+            for (int m = 0; m < KS_MB; ++m) part[m] = 0;
+            const int j0 = half ? 14 : 0, j1 = half ? KS_LEVELS : 14;
+#pragma unroll
+            for (int j = j0; j < j1; ++j) {
+                const i32 k = (i32)__ldg(row + (size_t)j * KSK_PAD);
+#pragma unroll
+                for (int m = 0; m < KS_MB; ++m) {
+                    const i32 d = j < KS_LEVELS - 1 ? ((w[m] >> j) & 1) - 1 : (w[m] >> (KS_LEVELS - 1));
+                    part[m] += d * k;
+                }
             }
+#pragma unroll
+            for (int m = 0; m < KS_MB; ++m) acc[m] += (i64)part[m];
         }
     }
     if (col > LWE2_N) return;
