@@ -382,6 +382,15 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     }
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<8, false>::SMEM));
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1_HALF_EXCLUSIVE_SMEM));
+    // always carve out the maximum shared memory for the big kernels: with the driver's default heuristic an occasional
+    // launch of l2_blind_rotate_kernel got a smaller carve-out and ran at 1 CTA/SM (278 ms instead of 215 ms for 2 368 messages)
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(pack_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(pack_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ctx->l1_half = getenv("OMR_L1_HALF") != nullptr;
     if (const char* e = getenv("OMR_OVERLAP")) ctx->overlap = atoi(e) != 0;
     if (const char* e = getenv("OMR_CHUNK")) { long v = atol(e); if (v >= 8) ctx->chunk = (size_t)v; }

@@ -106,7 +106,7 @@ template <class F> struct ArInt {
 // level 2 on the FP64 pipe (D2 in field.cuh).  Lazy ranges of the forward transform (|mulmod| < 0.76q, growth 0.76q per
 // stage): stages 0-5 from |x| <= 65 reach 4.6q (< 8q exact; mulmod inputs <= 3.8q), renormalise at the start of the pass
 // that begins at stage 6, stages 6-9 reach 3.6q, and the last stage renormalises its pass-through operand, so outputs
-// are <= 1.3q.  Inverse: inputs < 0.76q; sums are renormalised, differences (< 1.6q) go through mulmod.
+// are <= 1.3q.
 struct ArD2 {
     typedef double T; typedef double2 TW;
     static constexpr int LOGN = 11;
@@ -121,9 +121,14 @@ struct ArD2 {
         const T v = D2::mulmod(b, w.x, w.y);
         a = __dadd_rn(u, v); b = __dadd_rn(u, -v);
     }
+    // inverse: inputs <= 0.5q.  Sums are renormalised only after every second Gentleman-Sande stage (and after the last
+    // one): <= 0.66q -> 1.32q -> 2.64q stays below the 4q mulmod bound; differences always go through mulmod (< 0.67q).
     template <int STAGE> static __device__ __forceinline__ void inv(T& a, T& b, TW w) {
+        constexpr int done = LOGN - 1 - STAGE;                  // stages completed before this one
         const T u = a, v = b;
-        a = D2::renorm(__dadd_rn(u, v)); b = D2::mulmod(__dadd_rn(u, -v), w.x, w.y);
+        const T s = __dadd_rn(u, v);
+        a = ((done & 1) || done == LOGN - 1) ? D2::renorm(s) : s;
+        b = D2::mulmod(__dadd_rn(u, -v), w.x, w.y);
     }
 };
 // The twiddles of the first pass are the same for every thread (block index 0): they live in constant memory and reach
