@@ -205,6 +205,14 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in (h_a, h_b, h_p)) + n_pay * rp.cmb_count_per_cipher * D_BOARD * 2
     d2h = digest.numel() * 8
 
+    # ---- per-message detect latency (BASELINE.json configs[0]: --payload-count 1): one message, device time ------------
+    lat = []
+    for _ in range(3):
+        l0, l1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(); det.detect((clue_a[:1], clue_b[:1])); l1e.record(); torch.cuda.synchronize()
+        lat.append(l0.elapsed_time(l1e))
+    latency_ms = min(lat)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -247,6 +255,8 @@ def run_ours(args):
                    "vs_baseline_ref": "reference README.md:120-121, single-core detect 4.272 msg/s (unnamed AVX-512 CPU)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "messages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
         "gpu_launches": int(launches),
+        "latency": {"detect_one_message_ms": round(latency_ms, 3), "reference_ms": 243.6431,
+                    "note": "one message = one l1 CTA (7 of 8 groups) + one l2 CTA; reference: README.md:89-90, 1 thread"},
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "l2_blind_rotate_kernel", "achieved": round(hbm_achieved, 3), "peak": peaks.get("hbm_gbs"),
                      "unit": "GB/s", "frac": round(hbm_achieved / peaks.get("hbm_gbs"), 6), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

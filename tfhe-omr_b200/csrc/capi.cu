@@ -69,6 +69,7 @@ struct omr_ctx {
     u64* pv = nullptr; size_t pv_cap = 0, pv_count = 0; u64 pv_index0 = 0; bool pv_any = false;
     cudaEvent_t ev[5] = {};
     uint64_t launches = 0;
+    int n_sm = 148;
     bool l1_half = false;                         // L1 kernel shape for the stand-alone stage: <4, half tile> or <8, whole tile>
     // two-stream software pipeline of detect_device
     bool overlap = false; size_t chunk = 1184;   // measured slower than the plain sequence: off unless OMR_OVERLAP=1
@@ -151,7 +152,10 @@ int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* 
     const size_t n_clues = B * CLUE_COUNT;
     // exclusive_half: pad the request so that two such CTAs cannot share an SM but one of them plus one L2 CTA can
     const size_t smem_half = exclusive_half ? L1_HALF_EXCLUSIVE_SMEM : L1Cfg<4, true>::SMEM;
-    if (half)
+    // latency shape: with fewer blind rotations than SMs every rotation gets an SM of its own (one 64-thread group per CTA)
+    if (n_clues <= (size_t)ctx->n_sm && !half)
+        l1_blind_rotate_kernel<1, false><<<(unsigned)n_clues, L1Cfg<1, false>::THREADS, L1Cfg<1, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
+    else if (half)
         l1_blind_rotate_kernel<4, true><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4, true>::THREADS, smem_half, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     else
         l1_blind_rotate_kernel<8, false><<<(unsigned)((n_clues + 7) / 8), L1Cfg<8, false>::THREADS, L1Cfg<8, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
@@ -381,6 +385,8 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         CKC(cudaMemcpyToSymbol(c_tw2d_head, h2, sizeof h2));
     }
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<8, false>::SMEM));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<1, false>::SMEM));
+    { cudaDeviceProp prop; CKC(cudaGetDeviceProperties(&prop, device)); ctx->n_sm = prop.multiProcessorCount; }
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1_HALF_EXCLUSIVE_SMEM));
     // always carve out the maximum shared memory for the big kernels: with the driver's default heuristic an occasional
     // launch of l2_blind_rotate_kernel got a smaller carve-out and ran at 1 CTA/SM (278 ms instead of 215 ms for 2 368 messages)
