@@ -160,6 +160,12 @@ int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d_data, size_t batch, 
  * uses); the denominators of the compute roofline in bench.py. */
 int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_second);
 
+/* Launch shapes.  The reference detects one message per rayon task (examples/omr.rs:160-164), so a caller may hand over
+ * anything from one clue set to a whole board.  Batches with fewer messages than SMs default to latency shapes (one level-1
+ * blind rotation per CTA, key-switch rows split across CTAs, 512 threads per level-2 blind rotation); larger batches use
+ * the throughput shapes.  Both give bit-identical results; enable = 0 forces the throughput shapes for every batch size. */
+int omr_set_latency_shapes(omr_ctx* ctx, int enable);
+
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
 uint64_t omr_launch_count(const omr_ctx* ctx);
 

@@ -36,7 +36,15 @@ def test_ntt_forward_inverse_vs_oracle(detector):
         assert np.array_equal(d.cpu().numpy().view(x.dtype), x)
 
 
-def test_stages_bit_exact(detector, keypack, decoy):
+@pytest.fixture(params=["latency", "throughput"])
+def shape(request, detector):
+    """Small batches run the latency launch shapes by default; every stage is checked in both (omr_set_latency_shapes)."""
+    detector.set_latency_shapes(request.param == "latency")
+    yield request.param
+    detector.set_latency_shapes(True)
+
+
+def test_stages_bit_exact(detector, keypack, decoy, shape):
     import torch
     a, b = _mixed_clues(keypack, decoy, 3, [1])
     da, db = _dev(a, np.int16), _dev(b, np.int16)
@@ -55,6 +63,29 @@ def test_stages_bit_exact(detector, keypack, decoy):
     # whole pipeline in one call
     pv = detector.detect((a, b))
     assert np.array_equal(pv.to_host(), ref_tr)
+
+
+def test_launch_shapes_agree(detector, keypack):
+    """Latency and throughput shapes of every stage give identical words on random (not clue-shaped) inputs, including
+    batch sizes at the switch-over points (21 messages = 147 level-1 CTAs, 148 level-2 CTAs, 256 key-switch messages)."""
+    import torch
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 2048, (21, 512), dtype=np.uint16); b = rng.integers(0, 2048, (21, 7), dtype=np.uint16)
+    rl = rng.integers(0, O.Q1, (256, 2, O.N1), dtype=np.uint32)
+    lw = rng.integers(0, 4096, (148, 671), dtype=np.uint32)
+    got = {}
+    for lat in (True, False):
+        detector.set_latency_shapes(lat)
+        l1 = detector.first_level_blind_rotate(_dev(a, np.int16), _dev(b, np.int16))
+        ks = [detector.key_switch(_dev(rl[:n], np.int32)) for n in (1, 17, 256)]
+        l2 = [detector.second_level_blind_rotate(_dev(lw[:n], np.int32)) for n in (1, 148)]
+        torch.cuda.synchronize()
+        got[lat] = [l1.cpu().numpy()] + [k.cpu().numpy() for k in ks] + [x.cpu().numpy() for x in l2]
+    detector.set_latency_shapes(True)
+    for x, y in zip(got[True], got[False]):
+        assert np.array_equal(x, y)
+    # key switch of one message against the oracle on a random (full-range) ciphertext
+    assert np.array_equal(got[True][1].view(np.uint32).reshape(1, -1)[:, :671], keypack.keyswitch(rl[:1]))
 
 
 def test_omd_acceptance(detector, keypack, decoy):

@@ -61,6 +61,7 @@ struct omr_ctx {
     // scratch for the batched pipeline, sized for `cap` messages
     size_t cap = 0; u32* s_rlwe1 = nullptr; u32* s_lwe2 = nullptr; unsigned short *s_ca = nullptr, *s_cb = nullptr;
     size_t cap7 = 0; u32* s_rlwe7 = nullptr;      // per-(message, clue) accumulators of the L1 kernel
+    unsigned long long* ks_part = nullptr;        // [KS_SPLIT_MAXB][KSK_PAD] partial sums of the split key switch
     // packing scratch
     u64* s_partial = nullptr; size_t partial_words = 0;
     u64* s_digest = nullptr; size_t digest_words = 0;
@@ -70,6 +71,7 @@ struct omr_ctx {
     cudaEvent_t ev[5] = {};
     uint64_t launches = 0;
     int n_sm = 148;
+    bool latency_shapes = true;                   // omr_set_latency_shapes / OMR_LATENCY_SHAPES=0: throughput shapes for every batch size
     bool l1_half = false;                         // L1 kernel shape for the stand-alone stage: <4, half tile> or <8, whole tile>
     // two-stream software pipeline of detect_device
     bool overlap = false; size_t chunk = 1184;   // measured slower than the plain sequence: off unless OMR_OVERLAP=1
@@ -126,16 +128,32 @@ int launch_l1(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, 
     }
     return launch_l1_raw(ctx, ca, cb, B, ctx->s_rlwe7, out, ctx->l1_half, s);
 }
+constexpr size_t KS_SPLIT_MAXB = 256;
 int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s) {
     if (!B) return OMR_OK;
     dim3 grid((unsigned)((B + KS_MB - 1) / KS_MB), (KSK_PAD + KS_THREADS - 1) / KS_THREADS);
-    keyswitch_kernel<<<grid, KS_THREADS, KS_SMEM, s>>>(rlwe, ctx->ksk, out, (int)B);
+    if (B <= KS_SPLIT_MAXB && ctx->latency_shapes) {
+        // small batch: too few CTAs to fill the GPU and each walks 27 648 key rows serially -> split the rows
+        if (!ctx->ks_part) CK(cudaMalloc((void**)&ctx->ks_part, KS_SPLIT_MAXB * KSK_PAD * sizeof(unsigned long long)));
+        unsigned z = 1;
+        while (z < 64 && grid.x * grid.y * z < 2u * (unsigned)ctx->n_sm) z *= 2;
+        grid.z = z;
+        CK(cudaMemsetAsync(ctx->ks_part, 0, B * KSK_PAD * sizeof(unsigned long long), s));
+        keyswitch_kernel<true><<<grid, KS_THREADS, KS_SMEM, s>>>(rlwe, ctx->ksk, out, (int)B, ctx->ks_part);
+        keyswitch_finish_kernel<<<(unsigned)((B * KSK_PAD + 255) / 256), 256, 0, s>>>(rlwe, ctx->ks_part, out, (int)B);
+        ctx->launches += 2; CK(cudaGetLastError());
+        return OMR_OK;
+    }
+    keyswitch_kernel<false><<<grid, KS_THREADS, KS_SMEM, s>>>(rlwe, ctx->ksk, out, (int)B, nullptr);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
 int launch_l2(omr_ctx* ctx, const u32* lwe, size_t B, u64* out, cudaStream_t s) {
     if (!B) return OMR_OK;
-    l2_blind_rotate_kernel<<<(unsigned)B, L2_THREADS, L2_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out, ctx->tb);
+    if (B <= (size_t)ctx->n_sm && ctx->latency_shapes)         // fewer messages than SMs: 512 threads per message
+        l2_blind_rotate_lat_kernel<<<(unsigned)B, L2L_THREADS, L2L_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out, ctx->tb);
+    else
+        l2_blind_rotate_kernel<<<(unsigned)B, L2_THREADS, L2_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out, ctx->tb);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
@@ -153,7 +171,7 @@ int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* 
     // exclusive_half: pad the request so that two such CTAs cannot share an SM but one of them plus one L2 CTA can
     const size_t smem_half = exclusive_half ? L1_HALF_EXCLUSIVE_SMEM : L1Cfg<4, true>::SMEM;
     // latency shape: with fewer blind rotations than SMs every rotation gets an SM of its own (one 64-thread group per CTA)
-    if (n_clues <= (size_t)ctx->n_sm && !half)
+    if (n_clues <= (size_t)ctx->n_sm && !half && ctx->latency_shapes)
         l1_blind_rotate_kernel<1, false><<<(unsigned)n_clues, L1Cfg<1, false>::THREADS, L1Cfg<1, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     else if (half)
         l1_blind_rotate_kernel<4, true><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4, true>::THREADS, smem_half, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
@@ -394,14 +412,17 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CKC(cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(keyswitch_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(pack_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(pack_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ctx->l1_half = getenv("OMR_L1_HALF") != nullptr;
     if (const char* e = getenv("OMR_OVERLAP")) ctx->overlap = atoi(e) != 0;
+    if (const char* e = getenv("OMR_LATENCY_SHAPES")) ctx->latency_shapes = atoi(e) != 0;
     if (const char* e = getenv("OMR_CHUNK")) { long v = atol(e); if (v >= 8) ctx->chunk = (size_t)v; }
-    CKC(cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
+    CKC(cudaFuncSetAttribute(keyswitch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
+    CKC(cudaFuncSetAttribute(keyswitch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
     CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2_SMEM));
+    CKC(cudaFuncSetAttribute(l2_blind_rotate_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2L_SMEM));
     CKC(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM));
     // keys -> internal form: every ring word * (R * N^-1) mod q; KSK padded to a 672-word row stride
     const size_t n_bsk1 = (size_t)CLUE_N * 2 * G1::LEVELS * 2 * F1::N, n_ksk_rows = (size_t)F1::N * KS_LEVELS,
@@ -449,7 +470,7 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
-                    ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
+                    ctx->ks_part, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) { if (ctx->p_rlwe7[k]) cudaFree(ctx->p_rlwe7[k]); if (ctx->p_rlwe1[k]) cudaFree(ctx->p_rlwe1[k]); if (ctx->p_lwe2[k]) cudaFree(ctx->p_lwe2[k]); }
     for (auto& ev : ctx->pev) if (ev) cudaEventDestroy(ev);
@@ -463,6 +484,11 @@ void omr_ctx_destroy(omr_ctx* ctx) {
 const char* omr_last_error(const omr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 size_t omr_detect_key_size(const omr_ctx* ctx) { return ctx ? ctx->key_bytes : 0; }
 uint64_t omr_launch_count(const omr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int omr_set_latency_shapes(omr_ctx* ctx, int enable) {
+    if (!ctx) return OMR_ERR_INVALID;
+    ctx->latency_shapes = enable != 0;
+    return OMR_OK;
+}
 
 int omr_retrieval_params_init(uint64_t all_payloads_count, uint32_t pertinent_count, omr_retrieval_params* rp) {
     if (!rp) return OMR_ERR_INVALID;

@@ -315,6 +315,82 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
     for (int e = t; e < 2 * N; e += L2_THREADS) out[(size_t)msg * 2 * N + e] = acc[e];
 }
 
+// K3, latency shape (batches of at most one message per SM): 512 threads per message.  Half h (256 threads) decomposes
+// polynomial h of acc and runs its 6 digit transforms and their MACs; the halves swap one partial sum each through shared
+// memory, so half 0 finishes the a-polynomial and half 1 the b-polynomial (one inverse transform each).  All sums are
+// exact integers below 2^53 in both shapes, so the result is bit-identical to l2_blind_rotate_kernel.
+constexpr int L2L_THREADS = 2 * GeoL2::NT;
+constexpr size_t L2L_SMEM = (size_t)2 * F2::N * 8 + (size_t)4 * GeoL2::BUF * 8 + (size_t)2 * F2::N * 8 + F2::N * sizeof(double2) + 672 * sizeof(unsigned short);
+
+__global__ void __launch_bounds__(L2L_THREADS, 1)
+l2_blind_rotate_lat_kernel(const u32* __restrict__ lwe, const double* __restrict__ bsk2, u64* __restrict__ out, Tables tb) {
+    typedef F2 F; typedef G2 G; typedef GeoL2 GEO; typedef ArD2 AR;
+    constexpr int N = F::N, E = GEO::E, L = G::LEVELS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* acc = reinterpret_cast<u64*>(smem_raw);
+    double* bufs = reinterpret_cast<double*>(acc + 2 * N);
+    double* swp = bufs + 4 * GEO::BUF;                                   // [2][N] partial sums handed to the other half
+    double2* s_tw = reinterpret_cast<double2*>(swp + 2 * N);
+    unsigned short* la = reinterpret_cast<unsigned short*>(s_tw + N);
+    const int msg = blockIdx.x, h = threadIdx.x / GEO::NT, t = threadIdx.x % GEO::NT, bar = 1 + h;
+    double* bx = bufs + (size_t)h * 2 * GEO::BUF; double* by = bx + GEO::BUF;
+    for (int i = threadIdx.x; i < N; i += L2L_THREADS) s_tw[i] = tb.tw2d[i];
+    for (int i = threadIdx.x; i < LWE2_STRIDE_IN; i += L2L_THREADS) la[i] = (unsigned short)(lwe[(size_t)msg * LWE2_STRIDE_IN + i] & (LWE2_Q - 1));
+    __syncthreads();
+    if (h == 0) init_acc<F, GEO>(acc, tb.lut2, la[LWE2_N], t);
+    __syncthreads();
+#pragma unroll 1
+    for (int i = 0; i < LWE2_N; ++i) {
+        const int a = la[i];
+        if (a == 0) continue;
+        const double* key = bsk2 + ((size_t)i * 2 * L + (size_t)h * L) * 2 * N + out_idx<GEO>(t, 0);
+        double ma[E], mb[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) { ma[k] = 0.0; mb[k] = 0.0; }
+        i64 u[E];
+        decompose_words<F, G, GEO>(u, acc + h * N, a, t);
+#pragma unroll 1
+        for (int r = 0; r < L; r += 2) {
+            double x[E], y[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r));
+                y[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r + 1));
+            }
+            ntt_forward2s<AR, GEO, LdSharedC>(x, y, bx, by, s_tw, t, bar);
+            const double* kx = key + (size_t)r * 2 * N;
+#pragma unroll
+            for (int k = 0; k < E; k += 2) {
+                const int o = out_idx<GEO>(0, k) - out_idx<GEO>(0, 0);
+                const double2 xa = ld_stream_f64x2(kx + o), xb = ld_stream_f64x2(kx + N + o);
+                const double2 ya = ld_stream_f64x2(kx + 2 * N + o), yb = ld_stream_f64x2(kx + 3 * N + o);
+                ma[k] = __dadd_rn(ma[k], __dadd_rn(D2::mulmod_key(x[k], xa.x), D2::mulmod_key(y[k], ya.x)));
+                ma[k + 1] = __dadd_rn(ma[k + 1], __dadd_rn(D2::mulmod_key(x[k + 1], xa.y), D2::mulmod_key(y[k + 1], ya.y)));
+                mb[k] = __dadd_rn(mb[k], __dadd_rn(D2::mulmod_key(x[k], xb.x), D2::mulmod_key(y[k], yb.x)));
+                mb[k + 1] = __dadd_rn(mb[k + 1], __dadd_rn(D2::mulmod_key(x[k + 1], xb.y), D2::mulmod_key(y[k + 1], yb.y)));
+            }
+        }
+        // half 0 keeps the a-sums and hands over its b-sums, half 1 the other way round
+        double m[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) { m[k] = h ? mb[k] : ma[k]; swp[(size_t)h * N + t + GEO::NT * k] = h ? ma[k] : mb[k]; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < E; ++k) m[k] = D2::renorm(__dadd_rn(m[k], swp[(size_t)(1 - h) * N + t + GEO::NT * k]));
+        ExBuf<double> eb{bx, by};
+        ntt_inverse<AR, GEO, LdGlobal>(m, eb, tb.itw2d, t, bar);
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const int pos = h * N + t + GEO::NT * k;
+            i64 v = (i64)acc[pos] + D2::to_i64(m[k]);
+            v += v < 0 ? (i64)F::Q : 0; v -= v >= (i64)F::Q ? (i64)F::Q : 0;
+            acc[pos] = (u64)v;
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < 2 * N; e += L2L_THREADS) out[(size_t)msg * 2 * N + e] = acc[e];
+}
+
 // ---- K2: sample extraction + LWE key switch + modulus switch + offset ---------------------------------------------
 // out[col] = (0,..,0,b0) - SUM_{i<1024, j<27} d_ij * KSK[i][j][col]  (d = balanced base-2 digits of a'_i), then
 // x -> round(x * 4096 / q1) mod 4096, b += 7 * 128.   A {-1,0,1} x u32 integer product: thread = column,
@@ -322,8 +398,22 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
 constexpr int KS_MB = 16, KS_THREADS = 128;
 constexpr size_t KS_SMEM = (size_t)KS_MB * F1::N * sizeof(i32);
 
-__global__ void __launch_bounds__(KS_THREADS)
-keyswitch_kernel(const u32* __restrict__ rlwe, const u32* __restrict__ ksk, u32* __restrict__ out, int B) {
+// Final step of K2 for one (message, column): reduce, subtract from (0,..,0,b0), modulus switch, offset.
+__device__ __forceinline__ u32 ks_finish(i64 sum, u32 b0, int col) {
+    i64 s = sum % (i64)Q1; if (s < 0) s += Q1;
+    const u32 base = col == LWE2_N ? b0 : 0u;
+    const u32 x = base >= (u32)s ? base - (u32)s : base + Q1 - (u32)s;
+    u32 y = (u32)(((u64)2 * LWE2_Q * x + Q1) / (2ull * Q1)) & (LWE2_Q - 1);
+    if (col == LWE2_N) y = (y + CLUE_COUNT * (LWE2_Q >> 5)) & (LWE2_Q - 1);
+    return y;
+}
+
+// SPLIT = false: one CTA walks all 1024 key rows (throughput shape).  SPLIT = true (small batches): gridDim.z CTAs each
+// walk 1024 / gridDim.z rows and add their exact integer partial sums into `part` [B][KSK_PAD] (zeroed by the caller);
+// keyswitch_finish_kernel completes the step.  Integer addition commutes, so both shapes give identical words.
+template <bool SPLIT> __global__ void __launch_bounds__(KS_THREADS)
+keyswitch_kernel(const u32* __restrict__ rlwe, const u32* __restrict__ ksk, u32* __restrict__ out, int B,
+                 unsigned long long* __restrict__ part) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     i32 (*uw)[F1::N] = reinterpret_cast<i32 (*)[F1::N]>(smem_raw);        // [KS_MB][N] offset words
     const int m0 = blockIdx.x * KS_MB, col = blockIdx.y * KS_THREADS + threadIdx.x;
@@ -344,8 +434,9 @@ keyswitch_kernel(const u32* __restrict__ rlwe, const u32* __restrict__ ksk, u32*
     i64 acc[KS_MB];
 #pragma unroll
     for (int m = 0; m < KS_MB; ++m) acc[m] = 0;
+    const int rows = SPLIT ? F1::N / (int)gridDim.z : F1::N, i_lo = SPLIT ? (int)blockIdx.z * rows : 0;
 #pragma unroll 1
-    for (int i = 0; i < F1::N; ++i) {
+    for (int i = i_lo; i < i_lo + rows; ++i) {
         i32 w[KS_MB];
 #pragma unroll
         for (int m = 0; m < KS_MB; ++m) w[m] = uw[m][i];
@@ -375,13 +466,16 @@ keyswitch_kernel(const u32* __restrict__ rlwe, const u32* __restrict__ ksk, u32*
 #pragma unroll
     for (int m = 0; m < KS_MB; ++m) {
         if (m0 + m >= B) break;
-        i64 s = acc[m] % (i64)Q1; if (s < 0) s += Q1;
-        const u32 base = col == LWE2_N ? rlwe[(size_t)(m0 + m) * 2 * F1::N + F1::N] : 0u;   // b0
-        const u32 x = base >= (u32)s ? base - (u32)s : base + Q1 - (u32)s;
-        u32 y = (u32)(((u64)2 * LWE2_Q * x + Q1) / (2ull * Q1)) & (LWE2_Q - 1);
-        if (col == LWE2_N) y = (y + CLUE_COUNT * (LWE2_Q >> 5)) & (LWE2_Q - 1);
-        out[(size_t)(m0 + m) * LWE2_STRIDE_IN + col] = y;
+        if (SPLIT) atomicAdd(part + (size_t)(m0 + m) * KSK_PAD + col, (unsigned long long)acc[m]);
+        else out[(size_t)(m0 + m) * LWE2_STRIDE_IN + col] = ks_finish(acc[m], rlwe[(size_t)(m0 + m) * 2 * F1::N + F1::N], col);
     }
+}
+
+__global__ void keyswitch_finish_kernel(const u32* __restrict__ rlwe, const unsigned long long* __restrict__ part,
+                                        u32* __restrict__ out, int B) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, m = e / KSK_PAD, col = e % KSK_PAD;
+    if (m >= B || col > LWE2_N) return;
+    out[(size_t)m * LWE2_STRIDE_IN + col] = ks_finish((i64)part[e], rlwe[(size_t)m * 2 * F1::N + F1::N], col);
 }
 
 // ---- K4: scale by N^-1, homomorphic trace, forward NTT ----------------------------------------------------------------

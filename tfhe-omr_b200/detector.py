@@ -133,6 +133,10 @@ class Detector:
     def launch_count(self):
         return int(self.L.omr_launch_count(self.h))
 
+    def set_latency_shapes(self, enable):
+        """omr_set_latency_shapes: small batches use the latency launch shapes (default) or the throughput shapes."""
+        self._ck(self.L.omr_set_latency_shapes(self.h, 1 if enable else 0))
+
     def _stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 
