@@ -1,14 +1,16 @@
 """Experiment: do the integer level-1 kernel and the FP64 level-2 kernel overlap when one CTA of each shares an SM?
-Run with OMR_L1_HALF=1 OMR_L1_EXCL=1 OMR_L2_PAD=1 (each kernel then occupies half an SM)."""
+Run with OMR_L1_HALF=1: 147 level-1 CTAs (256 threads, 4 blind rotations each) and 148 level-2 CTAs (256 threads), one wave
+each, so that every SM holds one CTA of each kernel when both run."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from stage_times import random_detector
 det = random_detector()
-B = 592
+det.set_latency_shapes(False)
+B1, B = 84, 148
 g = torch.Generator(device="cuda"); g.manual_seed(1)
-a = torch.randint(0, 2048, (B, 512), dtype=torch.int16, device="cuda", generator=g)
-b = torch.randint(0, 2048, (B, 7), dtype=torch.int16, device="cuda", generator=g)
+a = torch.randint(0, 2048, (B1, 512), dtype=torch.int16, device="cuda", generator=g)
+b = torch.randint(0, 2048, (B1, 7), dtype=torch.int16, device="cuda", generator=g)
 lw = torch.randint(0, 4096, (B, 671), dtype=torch.int32, device="cuda", generator=g)
 sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
 def run(l1, l2):

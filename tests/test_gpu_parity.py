@@ -67,25 +67,26 @@ def test_stages_bit_exact(detector, keypack, decoy, shape):
 
 def test_launch_shapes_agree(detector, keypack):
     """Latency and throughput shapes of every stage give identical words on random (not clue-shaped) inputs, including
-    batch sizes at the switch-over points (21 messages = 147 level-1 CTAs, 148 level-2 CTAs, 256 key-switch messages)."""
+    batch sizes at the switch-over points (level 1: 21 / 22 / 43 messages = one rotation per CTA / two / four; level 2:
+    clusters up to ~24 messages, 512-thread CTAs up to 148; key switch: split rows up to 256 messages)."""
     import torch
     rng = np.random.default_rng(5)
-    a = rng.integers(0, 2048, (21, 512), dtype=np.uint16); b = rng.integers(0, 2048, (21, 7), dtype=np.uint16)
+    a = rng.integers(0, 2048, (43, 512), dtype=np.uint16); b = rng.integers(0, 2048, (43, 7), dtype=np.uint16)
     rl = rng.integers(0, O.Q1, (256, 2, O.N1), dtype=np.uint32)
     lw = rng.integers(0, 4096, (148, 671), dtype=np.uint32)
     got = {}
     for lat in (True, False):
         detector.set_latency_shapes(lat)
-        l1 = detector.first_level_blind_rotate(_dev(a, np.int16), _dev(b, np.int16))
+        l1 = [detector.first_level_blind_rotate(_dev(a[:n], np.int16), _dev(b[:n], np.int16)) for n in (21, 22, 43)]
         ks = [detector.key_switch(_dev(rl[:n], np.int32)) for n in (1, 17, 256)]
-        l2 = [detector.second_level_blind_rotate(_dev(lw[:n], np.int32)) for n in (1, 148)]
+        l2 = [detector.second_level_blind_rotate(_dev(lw[:n], np.int32)) for n in (1, 24, 25, 148)]
         torch.cuda.synchronize()
-        got[lat] = [l1.cpu().numpy()] + [k.cpu().numpy() for k in ks] + [x.cpu().numpy() for x in l2]
+        got[lat] = [x.cpu().numpy() for x in l1 + ks + l2]
     detector.set_latency_shapes(True)
     for x, y in zip(got[True], got[False]):
         assert np.array_equal(x, y)
     # key switch of one message against the oracle on a random (full-range) ciphertext
-    assert np.array_equal(got[True][1].view(np.uint32).reshape(1, -1)[:, :671], keypack.keyswitch(rl[:1]))
+    assert np.array_equal(got[True][3].view(np.uint32).reshape(1, -1)[:, :671], keypack.keyswitch(rl[:1]))
 
 
 def test_omd_acceptance(detector, keypack, decoy):

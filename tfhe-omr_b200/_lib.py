@@ -45,7 +45,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(tfhe_omr_b200 has no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(os.environ.get("OMR_B200_LIB", LIB_PATH))       # override: A/B runs of experimental builds (scripts/)
     vp, u64, u32, i32, sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
     P = C.POINTER
     L.omr_ctx_create.restype = i32; L.omr_ctx_create.argtypes = [i32, P(KeyBlobs), P(vp)]

@@ -61,6 +61,8 @@ struct omr_ctx {
     // scratch for the batched pipeline, sized for `cap` messages
     size_t cap = 0; u32* s_rlwe1 = nullptr; u32* s_lwe2 = nullptr; unsigned short *s_ca = nullptr, *s_cb = nullptr;
     size_t cap7 = 0; u32* s_rlwe7 = nullptr;      // per-(message, clue) accumulators of the L1 kernel
+    int l2c_max_clusters = 0;                     // co-resident 6-CTA clusters (cudaOccupancyMaxActiveClusters)
+    double* l2c_scratch = nullptr;                // partial sums exchanged inside a level-2 cluster
     unsigned long long* ks_part = nullptr;        // [KS_SPLIT_MAXB][KSK_PAD] partial sums of the split key switch
     // packing scratch
     u64* s_partial = nullptr; size_t partial_words = 0;
@@ -150,7 +152,12 @@ int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s)
 }
 int launch_l2(omr_ctx* ctx, const u32* lwe, size_t B, u64* out, cudaStream_t s) {
     if (!B) return OMR_OK;
-    if (B <= (size_t)ctx->n_sm && ctx->latency_shapes)         // fewer messages than SMs: 512 threads per message
+    if (B <= (size_t)ctx->l2c_max_clusters && ctx->latency_shapes) {      // a cluster of 6 SMs per message
+        const size_t cap = (size_t)ctx->l2c_max_clusters;
+        if (!ctx->l2c_scratch) CK(cudaMalloc((void**)&ctx->l2c_scratch, cap * L2C_SCRATCH_WORDS * sizeof(double)));
+        l2_blind_rotate_cluster_kernel<<<(unsigned)(B * L2C_CLUSTER), GeoL2::NT, L2C_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out,
+                                                                                                 ctx->l2c_scratch, ctx->tb);
+    } else if (B <= (size_t)ctx->n_sm && ctx->latency_shapes)  // fewer messages than SMs: 512 threads per message
         l2_blind_rotate_lat_kernel<<<(unsigned)B, L2L_THREADS, L2L_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out, ctx->tb);
     else
         l2_blind_rotate_kernel<<<(unsigned)B, L2_THREADS, L2_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out, ctx->tb);
@@ -170,11 +177,15 @@ int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* 
     const size_t n_clues = B * CLUE_COUNT;
     // exclusive_half: pad the request so that two such CTAs cannot share an SM but one of them plus one L2 CTA can
     const size_t smem_half = exclusive_half ? L1_HALF_EXCLUSIVE_SMEM : L1Cfg<4, true>::SMEM;
-    // latency shape: with fewer blind rotations than SMs every rotation gets an SM of its own (one 64-thread group per CTA)
+    // latency shape: with fewer blind rotations than SMs every rotation gets an SM of its own (8 groups share one rotation)
     if (n_clues <= (size_t)ctx->n_sm && !half && ctx->latency_shapes)
-        l1_blind_rotate_kernel<1, false><<<(unsigned)n_clues, L1Cfg<1, false>::THREADS, L1Cfg<1, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
+        l1_blind_rotate_lat_kernel<<<(unsigned)n_clues, L1L_THREADS, L1L_SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, ctx->tb);
     else if (half)
         l1_blind_rotate_kernel<4, true><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4, true>::THREADS, smem_half, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
+    else if (n_clues <= 2 * (size_t)ctx->n_sm && ctx->latency_shapes)      // mid-size batches: fewer rotations per CTA, every SM busy
+        l1_blind_rotate_kernel<2, false><<<(unsigned)((n_clues + 1) / 2), L1Cfg<2, false>::THREADS, L1Cfg<2, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
+    else if (n_clues <= 4 * (size_t)ctx->n_sm && ctx->latency_shapes)
+        l1_blind_rotate_kernel<4, false><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4, false>::THREADS, L1Cfg<4, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     else
         l1_blind_rotate_kernel<8, false><<<(unsigned)((n_clues + 7) / 8), L1Cfg<8, false>::THREADS, L1Cfg<8, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     ++ctx->launches; CK(cudaGetLastError());
@@ -403,7 +414,9 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         CKC(cudaMemcpyToSymbol(c_tw2d_head, h2, sizeof h2));
     }
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<8, false>::SMEM));
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<1, false>::SMEM));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1L_SMEM));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<2, false>::SMEM));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<4, false>::SMEM));
     { cudaDeviceProp prop; CKC(cudaGetDeviceProperties(&prop, device)); ctx->n_sm = prop.multiProcessorCount; }
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1_HALF_EXCLUSIVE_SMEM));
     // always carve out the maximum shared memory for the big kernels: with the driver's default heuristic an occasional
@@ -423,6 +436,18 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     CKC(cudaFuncSetAttribute(keyswitch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
     CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2_SMEM));
     CKC(cudaFuncSetAttribute(l2_blind_rotate_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2L_SMEM));
+    CKC(cudaFuncSetAttribute(l2_blind_rotate_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2C_SMEM));
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(L2C_CLUSTER * ctx->n_sm)); cfg.blockDim = dim3(GeoL2::NT); cfg.dynamicSmemBytes = L2C_SMEM;
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = L2C_CLUSTER; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, l2_blind_rotate_cluster_kernel, &cfg) != cudaSuccess) { nc = 0; cudaGetLastError(); }
+        // one CTA per SM is the point of the shape: never count more clusters than SMs / 6
+        ctx->l2c_max_clusters = nc < ctx->n_sm / L2C_CLUSTER ? nc : ctx->n_sm / L2C_CLUSTER;
+        if (const char* e = getenv("OMR_L2_CLUSTERS")) ctx->l2c_max_clusters = atoi(e);
+    }
     CKC(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM));
     // keys -> internal form: every ring word * (R * N^-1) mod q; KSK padded to a 672-word row stride
     const size_t n_bsk1 = (size_t)CLUE_N * 2 * G1::LEVELS * 2 * F1::N, n_ksk_rows = (size_t)F1::N * KS_LEVELS,
@@ -470,7 +495,7 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
-                    ctx->ks_part, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
+                    ctx->ks_part, ctx->l2c_scratch, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) { if (ctx->p_rlwe7[k]) cudaFree(ctx->p_rlwe7[k]); if (ctx->p_rlwe1[k]) cudaFree(ctx->p_rlwe1[k]); if (ctx->p_lwe2[k]) cudaFree(ctx->p_lwe2[k]); }
     for (auto& ev : ctx->pev) if (ev) cudaEventDestroy(ev);

@@ -224,6 +224,92 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
         for (int k = 0; k < 2 * E; ++k) o[t + GEO::NT * k] = acc[t + GEO::NT * k];
     }
 }
+// K1, latency shape (fewer blind rotations than SMs): one CTA per (message, clue), 8 groups of 64 threads.  Group g
+// transforms digit g & 3 of polynomial g >> 2 and multiplies it with its two key rows; the 8 partial products (REDC'd to
+// < 2q) are summed slice-wise by all 512 threads, then groups 0 and 1 run the two inverse transforms.  The critical path of
+// a CMux step is one forward and one inverse transform instead of eight and two; sums are exact mod q, so the accumulator
+// is bit-identical to the throughput shape.
+constexpr int L1L_GROUPS = 2 * G1::LEVELS, L1L_THREADS = L1L_GROUPS * L1_GROUP;
+constexpr size_t L1L_SMEM = (size_t)L1_TILE_WORDS * 4 + 2 * F1::N * sizeof(uint2) + (size_t)4 * F1::N * 4 +
+                            (size_t)L1L_GROUPS * 2 * GeoL1::BUF * 4 + CLUE_N * sizeof(unsigned short) + 16;
+static_assert(2 * GeoL1::BUF >= 2 * F1::N, "a group's exchange buffers hold its two partial products");
+
+__global__ void __launch_bounds__(L1L_THREADS, 1)
+l1_blind_rotate_lat_kernel(const unsigned short* __restrict__ clue_a, const unsigned short* __restrict__ clue_b,
+                           const u32* __restrict__ bsk1, u32* __restrict__ out /*[n_clues][2][N]*/, Tables tb) {
+    typedef F1 F; typedef G1 G; typedef GeoL1 GEO; typedef ArInt<F1> AR;
+    constexpr int N = F::N, E = GEO::E, L = G::LEVELS;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    u32* ktile = reinterpret_cast<u32*>(smem_dyn);
+    uint2* s_tw = reinterpret_cast<uint2*>(ktile + L1_TILE_WORDS);
+    uint2* s_itw = s_tw + N;
+    u32* acc = reinterpret_cast<u32*>(s_itw + N);            // [2][N]
+    u32* tot = acc + 2 * N;                                  // [2][N] summed products of the step
+    u32* bufs = tot + 2 * N;                                 // [8][2 * BUF]
+    unsigned short* ca = reinterpret_cast<unsigned short*>(bufs + (size_t)L1L_GROUPS * 2 * GEO::BUF);
+    u64* mbar = reinterpret_cast<u64*>(ca + CLUE_N);
+
+    const int g = threadIdx.x / L1_GROUP, t = threadIdx.x % L1_GROUP, bar = 1 + g;
+    const int cid = blockIdx.x, msg = cid / CLUE_COUNT, c = cid % CLUE_COUNT;
+    const int p = g / L, r = g % L;
+    u32* mine = bufs + (size_t)g * 2 * GEO::BUF;
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    for (int i = threadIdx.x; i < N; i += L1L_THREADS) { s_tw[i] = tb.tw1[i]; s_itw[i] = tb.itw1[i]; }
+    for (int i = threadIdx.x; i < CLUE_N; i += L1L_THREADS) ca[i] = clue_a[(size_t)msg * CLUE_N + i] & (CLUE_Q - 1);
+    if (g == 0) init_acc<F, GEO>(acc, tb.lut1, clue_b[(size_t)msg * CLUE_COUNT + c] & (CLUE_Q - 1), t);
+    __syncthreads();
+    if (threadIdx.x == 0) tma_load(ktile, bsk1, L1_TILE_WORDS * 4, mbar);
+#pragma unroll 1
+    for (int i = 0; i < CLUE_N; ++i) {
+        const int a = i <= c ? ca[c - i] : ((CLUE_Q - ca[CLUE_N + c - i]) & (CLUE_Q - 1));
+        i32 u[E];
+        decompose_words<F, G, GEO>(u, acc + p * N, a, t);
+        u32 x[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, G>(u[k], r);
+        ExBuf<u32> eb{mine, mine + GEO::BUF};
+        ntt_forward<AR, GEO, LdSharedC>(x, eb, s_tw, t, bar);
+        mbar_wait(mbar, i & 1);                                                  // tile i has landed
+        const u32* ka = ktile + (size_t)g * 2 * N + out_idx<GEO>(t, 0);
+        const u32* kb = ka + N;
+        group_sync<GEO::NT>(bar);                                                // the group's last exchange has been read
+#pragma unroll
+        for (int k = 0; k < E; k += 4) {
+            const int o = out_idx<GEO>(0, k) - out_idx<GEO>(0, 0);
+            const uint4 va = *reinterpret_cast<const uint4*>(ka + o), vb = *reinterpret_cast<const uint4*>(kb + o);
+            mine[t + GEO::NT * k] = F::redc((u64)x[k] * va.x); mine[t + GEO::NT * (k + 1)] = F::redc((u64)x[k + 1] * va.y);
+            mine[t + GEO::NT * (k + 2)] = F::redc((u64)x[k + 2] * va.z); mine[t + GEO::NT * (k + 3)] = F::redc((u64)x[k + 3] * va.w);
+            mine[N + t + GEO::NT * k] = F::redc((u64)x[k] * vb.x); mine[N + t + GEO::NT * (k + 1)] = F::redc((u64)x[k + 1] * vb.y);
+            mine[N + t + GEO::NT * (k + 2)] = F::redc((u64)x[k + 2] * vb.z); mine[N + t + GEO::NT * (k + 3)] = F::redc((u64)x[k + 3] * vb.w);
+        }
+        __syncthreads();                                                         // products visible; tile i is free
+        if (threadIdx.x == 0 && i + 1 < CLUE_N) tma_load(ktile, bsk1 + (size_t)(i + 1) * L1_TILE_WORDS, L1_TILE_WORDS * 4, mbar);
+#pragma unroll
+        for (int j = 0; j < 2 * N / L1L_THREADS; ++j) {
+            const int e = threadIdx.x + L1L_THREADS * j;
+            u32 sum = 0;                                                         // 8 terms < 2q each
+#pragma unroll
+            for (int gg = 0; gg < L1L_GROUPS; ++gg) sum += bufs[(size_t)gg * 2 * GEO::BUF + e];
+            tot[e] = F::inv_prepare(sum);
+        }
+        __syncthreads();
+        if (g < 2) {
+            u32 y[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) y[k] = tot[g * N + t + GEO::NT * k];
+            ExBuf<u32> ei{mine, mine + GEO::BUF};
+            ntt_inverse<AR, GEO, LdShared>(y, ei, s_itw, t, bar);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const int pos = g * N + t + GEO::NT * k;
+                acc[pos] = F::add_canon(acc[pos], y[k]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < 2 * N; e += L1L_THREADS) out[(size_t)cid * 2 * N + e] = acc[e];
+}
+
 // sum of the 7 accumulators of each message (detector.rs:556)
 __global__ void sum7_kernel(const u32* __restrict__ in /*[B*7][2][N]*/, u32* __restrict__ out /*[B][2][N]*/, size_t B) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,6 +475,102 @@ l2_blind_rotate_lat_kernel(const u32* __restrict__ lwe, const double* __restrict
         __syncthreads();
     }
     for (int e = threadIdx.x; e < 2 * N; e += L2L_THREADS) out[(size_t)msg * 2 * N + e] = acc[e];
+}
+
+// K3, cluster shape (at most n_sm / 6 messages): one thread-block cluster of 6 CTAs (6 SMs) per message.  CTA c holds
+// polynomial c / 3 of the accumulator, transforms digits 2(c % 3) and 2(c % 3) + 1 of it and multiplies them with their
+// key rows; the 6 partial sums are exchanged through a double-buffered global scratch (L2-resident) around ONE cluster
+// barrier per CMux step, and the three CTAs of a polynomial each run its inverse transform (redundantly, so no broadcast
+// is needed).  Critical path per step: one transform pair and one inverse instead of six pairs and one inverse pair.
+constexpr int L2C_CLUSTER = 6;
+constexpr size_t L2C_SMEM = (size_t)F2::N * 8 + (size_t)2 * GeoL2::BUF * 8 + F2::N * sizeof(double2) + 672 * sizeof(unsigned short);
+constexpr size_t L2C_SCRATCH_WORDS = (size_t)2 * L2C_CLUSTER * 2 * F2::N;          // doubles per message
+
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(L2C_CLUSTER, 1, 1) __launch_bounds__(GeoL2::NT, 1)
+l2_blind_rotate_cluster_kernel(const u32* __restrict__ lwe, const double* __restrict__ bsk2, u64* __restrict__ out,
+                               double* __restrict__ scratch, Tables tb) {
+    typedef F2 F; typedef G2 G; typedef GeoL2 GEO; typedef ArD2 AR;
+    constexpr int N = F::N, E = GEO::E, L = G::LEVELS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* acc = reinterpret_cast<u64*>(smem_raw);                         // polynomial p only
+    double* bx = reinterpret_cast<double*>(acc + N); double* by = bx + GEO::BUF;
+    double2* s_tw = reinterpret_cast<double2*>(by + GEO::BUF);
+    unsigned short* la = reinterpret_cast<unsigned short*>(s_tw + N);
+    const int msg = blockIdx.x / L2C_CLUSTER, c = blockIdx.x % L2C_CLUSTER, t = threadIdx.x;
+    const int p = c / 3, r0 = 2 * (c % 3);
+    double* scr = scratch + (size_t)msg * L2C_SCRATCH_WORDS;
+    for (int i = t; i < N; i += GEO::NT) s_tw[i] = tb.tw2d[i];
+    for (int i = t; i < LWE2_STRIDE_IN; i += GEO::NT) la[i] = (unsigned short)(lwe[(size_t)msg * LWE2_STRIDE_IN + i] & (LWE2_Q - 1));
+    __syncthreads();
+    {
+        const int rot = (2 * N - la[LWE2_N]) % (2 * N);                  // acc = (0, LUT * X^(2N - b))
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const int pos = t + GEO::NT * k;
+            const i64 v = rotated<F>(tb.lut2, pos, rot);
+            acc[pos] = p ? (u64)(v < 0 ? v + (i64)F::Q : v) : 0;
+        }
+    }
+    __syncthreads();
+    int par = 0;
+#pragma unroll 1
+    for (int i = 0; i < LWE2_N; ++i) {
+        const int a = la[i];
+        if (a == 0) continue;                                  // uniform over the cluster
+        const double* kx = bsk2 + ((size_t)i * 2 * L + (size_t)p * L + r0) * 2 * N + out_idx<GEO>(t, 0);
+        i64 u[E];
+        decompose_words<F, G, GEO>(u, acc, a, t);
+        double x[E], y[E], ma[E], mb[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r0));
+            y[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r0 + 1));
+        }
+        ntt_forward2s<AR, GEO, LdSharedC>(x, y, bx, by, s_tw, t, 0);
+#pragma unroll
+        for (int k = 0; k < E; k += 2) {
+            const int o = out_idx<GEO>(0, k) - out_idx<GEO>(0, 0);
+            const double2 xa = ld_stream_f64x2(kx + o), xb = ld_stream_f64x2(kx + N + o);
+            const double2 ya = ld_stream_f64x2(kx + 2 * N + o), yb = ld_stream_f64x2(kx + 3 * N + o);
+            ma[k] = __dadd_rn(D2::mulmod_key(x[k], xa.x), D2::mulmod_key(y[k], ya.x));
+            ma[k + 1] = __dadd_rn(D2::mulmod_key(x[k + 1], xa.y), D2::mulmod_key(y[k + 1], ya.y));
+            mb[k] = __dadd_rn(D2::mulmod_key(x[k], xb.x), D2::mulmod_key(y[k], yb.x));
+            mb[k + 1] = __dadd_rn(D2::mulmod_key(x[k + 1], xb.y), D2::mulmod_key(y[k + 1], yb.y));
+        }
+        double* w = scr + ((size_t)par * L2C_CLUSTER + c) * 2 * N;
+#pragma unroll
+        for (int k = 0; k < E; ++k) { __stcg(w + t + GEO::NT * k, ma[k]); __stcg(w + N + t + GEO::NT * k, mb[k]); }
+        cluster_barrier();
+        double m[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) m[k] = p ? mb[k] : ma[k];
+#pragma unroll
+        for (int cc = 1; cc < L2C_CLUSTER; ++cc) {
+            const int src = (c + cc) % L2C_CLUSTER;
+            const double* rd = scr + ((size_t)par * L2C_CLUSTER + src) * 2 * N + (size_t)p * N;
+#pragma unroll
+            for (int k = 0; k < E; ++k) m[k] = __dadd_rn(m[k], __ldcg(rd + t + GEO::NT * k));   // 12 terms x 0.66q < 2^53: exact
+        }
+#pragma unroll
+        for (int k = 0; k < E; ++k) m[k] = D2::renorm(m[k]);
+        ExBuf<double> eb{bx, by};
+        ntt_inverse<AR, GEO, LdGlobal>(m, eb, tb.itw2d, t, 0);
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const int pos = t + GEO::NT * k;
+            i64 v = (i64)acc[pos] + D2::to_i64(m[k]);
+            v += v < 0 ? (i64)F::Q : 0; v -= v >= (i64)F::Q ? (i64)F::Q : 0;
+            acc[pos] = (u64)v;
+        }
+        __syncthreads();
+        par ^= 1;
+    }
+    if (c % 3 == 0)
+        for (int e = t; e < N; e += GEO::NT) out[(size_t)msg * 2 * N + (size_t)p * N + e] = acc[e];
 }
 
 // ---- K2: sample extraction + LWE key switch + modulus switch + offset ---------------------------------------------
