@@ -212,6 +212,14 @@ def run_ours(args):
         l0.record(); det.detect((clue_a[:1], clue_b[:1])); l1e.record(); torch.cuda.synchronize()
         lat.append(l0.elapsed_time(l1e))
     latency_ms = min(lat)
+    # the same through the host-buffer C ABI (omr_detect_batch: clue in host memory -> pertinency vector in host memory)
+    h1a, h1b = clue_a[:1].cpu().numpy().view(np.uint16), clue_b[:1].cpu().numpy().view(np.uint16)
+    lat_host = []
+    for _ in range(3):
+        det.pv_reset(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); det.detect_host(h1a, h1b, want_pv=True); lat_host.append((time.perf_counter() - t0) * 1e3)
+    det.pv_reset()
+    latency_host_ms = min(lat_host)
 
     if rank != 0:
         if world > 1:
@@ -255,7 +263,7 @@ def run_ours(args):
                    "vs_baseline_ref": "reference README.md:120-121, single-core detect 4.272 msg/s (unnamed AVX-512 CPU)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "messages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
         "gpu_launches": int(launches),
-        "latency": {"detect_one_message_ms": round(latency_ms, 3), "reference_ms": 243.6431,
+        "latency": {"detect_one_message_ms": round(latency_ms, 3), "detect_one_message_host_api_ms": round(latency_host_ms, 3), "reference_ms": 243.6431,
                     "note": "latency shapes: 7 level-1 CTAs (8 groups per rotation), split key switch, one 6-CTA cluster for level 2; reference: README.md:89-90, 1 thread"},
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "l2_blind_rotate_kernel", "achieved": round(hbm_achieved, 3), "peak": peaks.get("hbm_gbs"),
