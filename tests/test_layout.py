@@ -1,50 +1,54 @@
-"""Python model of the NTT pass geometry and exchange-buffer swizzles of csrc/ntt.cuh: every pass is a partition of
-the N coefficients and every warp-wide shared-memory access is bank-conflict free."""
+"""Python model of the NTT pass geometry and padded exchange layouts of csrc/ntt.cuh (GeoL1 / GeoL2): the model's
+configuration is read from the typedefs in the header, every pass is a partition of the N coefficients, per-thread
+shared-memory offsets are thread-independent constants, every warp-wide access is bank-conflict free, and the multi-pass
+register schedule computes the oracle's Cooley-Tukey transform."""
+import os
+import re
+import sys
+
 import numpy as np
 import pytest
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import layout_check as LC  # noqa: E402
 
-def swz1(x):
-    return x ^ ((((x >> 5) & 1) * 3) | (((x >> 6) & 1) * 4) | (((x >> 7) & 1) * 24))
-
-
-def swz2(x):
-    return x ^ (((x >> 4) & 1) | (((x >> 5) & 1) * 6) | (((x >> 6) & 1) * 8))
+FIELDS = {"L1": (134215681, 4073518), "L2": (1125899906826241, 765727830662934)}
 
 
-def idx(N, logn, p, t, k):
-    NT = N // 8
-    ns = 3 if p < 3 else logn - 9
-    s0 = 3 * p
-    EP = 1 << ns
-    blk = N >> s0
-    stride = blk // EP
-    g, kk = divmod(k, EP)
-    vt = t + NT * g
-    j, i = divmod(vt, stride)
-    return j * blk + i + kk * stride
+def _header_config(name):
+    src = open(os.path.join(ROOT, "tfhe-omr_b200", "csrc", "ntt.cuh")).read()
+    m = re.search(r"typedef GeoT<([^>]*)>\s+Geo%s;" % name, src)
+    v = [int(x) for x in m.group(1).split(",")]
+    N, logn, NT, E, npass = v[:5]
+    ns = v[5:5 + npass]
+    pads = [(v[9 + 2 * x], v[10 + 2 * x]) for x in range(npass - 1)]
+    assert N == 1 << logn and NT * E == N and sum(ns) == logn
+    return N, NT, E, ns, pads
 
 
-@pytest.mark.parametrize("N,logn,swz,lanes,width", [(1024, 10, swz1, 32, 4), (2048, 11, swz2, 16, 8)])
-def test_pass_partition_and_bank_conflicts(N, logn, swz, lanes, width):
-    NT = N // 8
-    assert sorted(swz(x) for x in range(N)) == list(range(N))           # the swizzle is a permutation
-    for p in range(4):
-        seen = sorted(idx(N, logn, p, t, k) for t in range(NT) for k in range(8))
-        assert seen == list(range(N))
-        for k in range(8):
-            for w0 in range(0, NT, lanes):                                 # one (half-)warp per shared-memory transaction
-                addrs = [swz(idx(N, logn, p, t, k)) * width for t in range(w0, w0 + lanes)]
-                banks = [(a // width) % (128 // width) for a in addrs]
-                assert len(set(banks)) == lanes, (p, k, w0)
+@pytest.mark.parametrize("name", ["L1", "L2"])
+def test_model_matches_header(name):
+    N, NT, E, ns, pads = _header_config(name)
+    cfg = LC.CONFIGS[name]
+    assert (cfg[0], cfg[1], cfg[2], cfg[3], cfg[5]) == (N, NT, E, ns, pads)
 
 
-def test_bitrev_butterfly_schedule_matches_reference_ntt():
-    """the 4-pass register schedule computes the same in-place Cooley-Tukey transform as the oracle's loop nest"""
-    N, logn, q = 1024, 10, 134215681
-    psi = 4073518
+@pytest.mark.parametrize("name", ["L1", "L2"])
+def test_pass_partition_offsets_and_bank_conflicts(name, capsys):
+    assert LC.check(name)                                  # asserts partitions / constant offsets, returns conflict-freedom
+
+
+@pytest.mark.parametrize("name", ["L1", "L2"])
+def test_register_schedule_matches_reference_ntt(name):
+    """the multi-pass register schedule (Pass<GEO,P>::idx, twiddle index (1 << (s0+l)) + (j << l) + sb) computes the same
+    in-place Cooley-Tukey transform as the oracle's loop nest (natural in, bit-reversed out)"""
+    cfg = LC.CONFIGS[name]
+    N, NT, E, ns = cfg[:4]
+    logn = N.bit_length() - 1
+    q, psi = FIELDS[name]
     rng = np.random.default_rng(0)
-    a = [int(v) for v in rng.integers(0, q, N)]
+    a = [int(v) for v in rng.integers(0, 1 << 26, N)]
     brv = lambda x, b: int(format(x, f"0{b}b")[::-1], 2)
     tw = [pow(psi, brv(i, logn), q) for i in range(N)]
     ref = a[:]
@@ -57,16 +61,14 @@ def test_bitrev_butterfly_schedule_matches_reference_ntt():
                 ref[j], ref[j + t] = (u + v) % q, (u - v) % q
         m <<= 1
     x = a[:]
-    NT = N // 8
-    for p in range(4):
-        ns = 3 if p < 3 else logn - 9
-        s0, EP = 3 * p, 1 << ns
+    for p in range(len(ns)):
+        s0, EP = sum(ns[:p]), 1 << ns[p]
         stride = (N >> s0) // EP
         for tt in range(NT):
-            for g in range(8 // EP):
+            for g in range(E // EP):
                 j = (tt + NT * g) // stride
-                pos = [idx(N, logn, p, tt, g * EP + kk) for kk in range(EP)]
-                for l in range(ns):
+                pos = [LC.idx(cfg, p, tt, g * EP + kk) for kk in range(EP)]
+                for l in range(ns[p]):
                     half = EP >> (l + 1)
                     for sb in range(1 << l):
                         w = tw[(1 << (s0 + l)) + (j << l) + sb]
