@@ -309,11 +309,18 @@ def cpu_baseline(key_host, args, steps=1, native=True):
     rng = np.random.default_rng(3)
     a = rng.integers(0, 2048, (sample, 512), dtype=np.uint16); b = rng.integers(0, 2048, (sample, 7), dtype=np.uint16)
     t0 = time.perf_counter(); kp.detect(a[:1], b[:1], threads=1); t1 = time.perf_counter() - t0
+    # single-thread split under the stage names of benches/two_level_bs.rs:47-145
+    stage = {}
+    t0 = time.perf_counter(); r1 = kp.l1(a[:1], b[:1], threads=1); stage["first_level_blind_rotate_ms"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); lw = kp.keyswitch(r1, threads=1); stage["key_switch_ms"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); r2 = kp.l2(lw, threads=1); stage["second_level_blind_rotate_ms"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); kp.trace(r2, threads=1); stage["trace_ms"] = (time.perf_counter() - t0) * 1e3
     best = None
     for _ in range(steps):
         t0 = time.perf_counter(); kp.detect(a, b, threads=cores); dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return {"value": round(sample / best, 3), "unit": "messages/s", "cores": cores, "kind": "port",
+            "single_thread_stage_ms": {k: round(v, 1) for k, v in stage.items()},
             "sample": f"oracle detect (C++ port of detector.rs:135-166, {'-march=native' if native else 'portable'} build) on {sample} messages, "
                       f"{cores} threads; single-thread latency {t1 * 1e3:.0f} ms/message; packing not included (0.2% of the reference's time)",
             "single_thread_ms_per_message": round(t1 * 1e3, 1)}
