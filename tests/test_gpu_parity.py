@@ -79,7 +79,7 @@ def test_launch_shapes_agree(detector, keypack):
         detector.set_latency_shapes(lat)
         l1 = [detector.first_level_blind_rotate(_dev(a[:n], np.int16), _dev(b[:n], np.int16)) for n in (21, 22, 43)]
         ks = [detector.key_switch(_dev(rl[:n], np.int32)) for n in (1, 17, 256)]
-        l2 = [detector.second_level_blind_rotate(_dev(lw[:n], np.int32)) for n in (1, 24, 25, 148)]
+        l2 = [detector.second_level_blind_rotate(_dev(lw[:n], np.int32)) for n in (1, 24, 47, 148)]
         torch.cuda.synchronize()
         got[lat] = [x.cpu().numpy() for x in l1 + ks + l2]
     detector.set_latency_shapes(True)

@@ -152,8 +152,9 @@ int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s)
 }
 int launch_l2(omr_ctx* ctx, const u32* lwe, size_t B, u64* out, cudaStream_t s) {
     if (!B) return OMR_OK;
-    if (B <= (size_t)ctx->l2c_max_clusters && ctx->latency_shapes) {      // a cluster of 6 SMs per message
-        const size_t cap = (size_t)ctx->l2c_max_clusters;
+    // a cluster of 6 SMs per message: one wave of clusters takes ~1/3 of the time of the 512-thread shape, so up to two waves win
+    if (B <= 2 * (size_t)ctx->l2c_max_clusters && ctx->latency_shapes) {
+        const size_t cap = 2 * (size_t)ctx->l2c_max_clusters;
         if (!ctx->l2c_scratch) CK(cudaMalloc((void**)&ctx->l2c_scratch, cap * L2C_SCRATCH_WORDS * sizeof(double)));
         l2_blind_rotate_cluster_kernel<<<(unsigned)(B * L2C_CLUSTER), GeoL2::NT, L2C_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out,
                                                                                                  ctx->l2c_scratch, ctx->tb);
