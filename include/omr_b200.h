@@ -12,6 +12,11 @@
  *   negacyclic NTT: forward = Cooley-Tukey, natural order in, bit-reversed order out, out[k] = a(psi^(2*brv(k)+1)),
  *     psi1 = 4073518 (mod q1 = 134215681, N1 = 1024), psi2 = 765727830662934 (mod q2 = 1125899906826241, N2 = 2048).
  *   RLWE (a, b): b = a*s + m + e.   RGSW rows: [0,L) = RLWE(-s*m*g_j), [L,2L) = RLWE(m*g_j), g_j = 2^(drop + w*j).
+ *
+ * Concurrency.  The reference shares one `&Detector` between rayon workers (examples/omr.rs:160-164); here the batch IS the
+ * parallelism.  The host-buffer calls (omr_detect_batch, omr_encode_*) take the context's mutex and may be called from any
+ * thread.  The *_device calls use scratch buffers owned by the context: calls on one context must be ordered on ONE stream
+ * (or externally serialised); use one context per stream — or per recipient key — for concurrent work on a GPU.
  */
 #ifndef OMR_B200_H
 #define OMR_B200_H
