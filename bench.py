@@ -269,7 +269,11 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "l2_blind_rotate_kernel", "achieved": round(hbm_achieved, 3), "peak": peaks.get("hbm_gbs"),
                      "unit": "GB/s", "frac": round(hbm_achieved / peaks.get("hbm_gbs"), 6), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel_ms_per_launch": round(l2_ms, 3), "kernel_share_of_step": round(l2_ms / ms_per_step, 3),
-                     "note": "compute bound (FP64 / integer issue), not HBM bound: see roofline_compute"},
+                     "algorithmic_bytes": int(alg_bytes),
+                     "design_min_bytes": int(BSK2_BYTES * (-(-M // (2 * n_sm))) + M * (671 * 4 + 2 * 2048 * 8)),
+                     "note": "compute bound (FP64 / integer issue), not HBM bound: see roofline_compute.  algorithmic = one pass over BSK2 per "
+                             "launch; the accumulators live in shared memory (2 messages per SM), so this design re-streams BSK2 once per wave "
+                             "of 2 x n_sm messages (design_min_bytes); traffic / design_min = the re-reads caused by CTAs drifting apart"},
         "roofline_compute": {
             "bound": "fp64+int pipes", "achieved": round(1.0 / t_meas, 1), "peak": round(1.0 / t_roof, 1), "unit": "messages/s/GPU",
             "frac": round(t_roof / t_meas, 4),
