@@ -12,4 +12,5 @@ lw = torch.randint(0, 4096, (B, 671), dtype=torch.int32, device="cuda", generato
 out = det.second_level_blind_rotate(lw); torch.cuda.synchronize()
 t2 = [timed(lambda: det.second_level_blind_rotate(lw))[0] for _ in range(3)]
 t1 = [timed(lambda: det.first_level_blind_rotate(a, b))[0] for _ in range(2)]
-print(os.environ.get("OMR_B200_LIB", "default"), "l2", [round(x, 1) for x in t2], "l1", [round(x, 1) for x in t1], "checksum", int(out.sum().item()) & 0xffffff)
+o1 = det.first_level_blind_rotate(a, b); torch.cuda.synchronize()
+print(os.environ.get("OMR_B200_LIB", "default"), "l2", [round(x, 1) for x in t2], "l1", [round(x, 1) for x in t1], "checksum", int(out.sum().item()) & 0xffffff, int(o1.to(torch.int64).sum().item()) & 0xffffff)
