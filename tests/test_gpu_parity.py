@@ -89,6 +89,61 @@ def test_launch_shapes_agree(detector, keypack):
     assert np.array_equal(got[True][3].view(np.uint32).reshape(1, -1)[:, :671], keypack.keyswitch(rl[:1]))
 
 
+def test_small_batch_exchanges_repeatable(detector):
+    """The small-batch kernels exchange partial sums between groups / CTAs (shared memory in level 1, a double-buffered
+    global scratch around a cluster barrier in level 2, integer atomics in the key switch): 12 repetitions at one and two
+    waves of clusters must reproduce the throughput kernels' words every time (compute-sanitizer is not available on the
+    pool; a missed barrier shows up here as a flaky word)."""
+    import torch
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 2048, (3, 512), dtype=np.uint16); b = rng.integers(0, 2048, (3, 7), dtype=np.uint16)
+    lw = rng.integers(0, 4096, (44, 671), dtype=np.uint32)
+    rl = rng.integers(0, O.Q1, (40, 2, O.N1), dtype=np.uint32)
+    da, db, dlw, drl = _dev(a, np.int16), _dev(b, np.int16), _dev(lw, np.int32), _dev(rl, np.int32)
+    detector.set_latency_shapes(False)
+    want = [detector.first_level_blind_rotate(da, db), detector.second_level_blind_rotate(dlw[:22]), detector.second_level_blind_rotate(dlw),
+            detector.key_switch(drl)]
+    torch.cuda.synchronize()
+    detector.set_latency_shapes(True)
+    for _ in range(12):
+        got = [detector.first_level_blind_rotate(da, db), detector.second_level_blind_rotate(dlw[:22]), detector.second_level_blind_rotate(dlw),
+               detector.key_switch(drl)]
+        torch.cuda.synchronize()
+        for x, y in zip(got, want):
+            assert torch.equal(x, y)
+
+
+def test_extreme_inputs_bit_exact(detector, keypack, shape):
+    """Degenerate and saturated inputs through every stage: all-zero clues (every monomial is X^0: the skip path of the
+    level-2 kernels, the not-skipped identity CMux of level 1), all-maximal values, a single non-zero coefficient, and
+    non-canonical words (bits above the modulus are ignored, as `CmLwe<u16>` / `Lwe<u32>` values are canonical upstream)."""
+    import torch
+    a = np.zeros((4, 512), np.uint16); b = np.zeros((4, 7), np.uint16)
+    a[1] = 2047; b[1] = 2047
+    a[2, 0] = 1; b[2, 3] = 1024
+    a[3, ::2] = 2047; a[3, 1::2] = 1; b[3] = np.arange(7) * 293
+    ref_l1 = keypack.l1(a, b)
+    l1 = detector.first_level_blind_rotate(_dev(a, np.int16), _dev(b, np.int16)); torch.cuda.synchronize()
+    assert np.array_equal(l1.cpu().numpy().view(np.uint32), ref_l1)
+    noisy = detector.first_level_blind_rotate(_dev(a | 0xF800, np.int16), _dev(b | 0x8000, np.int16)); torch.cuda.synchronize()
+    assert np.array_equal(noisy.cpu().numpy(), l1.cpu().numpy())
+    lw = np.zeros((4, 671), np.uint32)
+    lw[1] = 4095
+    lw[2, 669] = 2048; lw[2, 670] = 4095
+    lw[3, ::3] = 1; lw[3, 670] = 2047
+    ref_l2 = keypack.l2(lw)
+    l2 = detector.second_level_blind_rotate(_dev(lw, np.int32)); torch.cuda.synchronize()
+    assert np.array_equal(l2.cpu().numpy().view(np.uint64), ref_l2)
+    l2n = detector.second_level_blind_rotate(_dev(lw | 0xFFFFF000, np.int32)); torch.cuda.synchronize()
+    assert np.array_equal(l2n.cpu().numpy(), l2.cpu().numpy())
+    # key switch of saturated accumulators (every coefficient q1 - 1, then 0) and the trace of the level-2 outputs
+    rl = np.full((2, 2, O.N1), O.Q1 - 1, np.uint32); rl[1] = 0
+    ks = detector.key_switch(_dev(rl, np.int32)); torch.cuda.synchronize()
+    assert np.array_equal(ks.cpu().numpy().view(np.uint32), keypack.keyswitch(rl))
+    tr = detector.trace(l2.clone()); torch.cuda.synchronize()
+    assert np.array_equal(tr.cpu().numpy().view(np.uint64), keypack.trace(ref_l2))
+
+
 def test_omd_acceptance(detector, keypack, decoy):
     """omr_core/examples/omd.rs:45-58: pertinent -> [1,0,...,0], non-pertinent -> all 0."""
     a, b = _mixed_clues(keypack, decoy, 2, [0], seed=21)
