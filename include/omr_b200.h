@@ -141,6 +141,18 @@ int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, si
 int omr_decrypt_decode_device(omr_ctx* ctx, const uint64_t* d_z2_ntt /*[2048]*/, const uint64_t* d_ct /*[n][2][2048]*/, size_t n,
                               uint16_t* d_out /*[n][2048]*/, void* stream);
 
+/* Retriever::decode_digest (retriever.rs:188-260), host buffers: decrypt and decode the index and payload ciphertexts on
+ * the GPU, scan the buckets (a bucket counts when its flag slot is exactly 1), look the found columns up in `weights`
+ * [combination_count][weight_stride] (the matrix the reference regenerates from its 32-byte seed, :215-226) and solve the
+ * system mod 257 (solve_matrix_mod_257, matrix.rs:164-247).  indices_out [pertinent_count] (sorted), *n_found, payloads_out
+ * [pertinent_count][612].  A singular system returns OMR_ERR_INVALID with "matrix is not invertible" (OmrError::
+ * InvertibleMatrix, error.rs:4-8). */
+int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* z2_ntt /*[2048]*/,
+                      const uint64_t* index_cts /*[n_index_cts][2][2048]*/, uint32_t n_index_cts,
+                      const uint64_t* payload_cts /*[n_payload_cts][2][2048]*/, uint32_t n_payload_cts,
+                      const uint16_t* weights, size_t weight_stride,
+                      uint64_t* indices_out, uint32_t* n_found, uint16_t* payloads_out);
+
 /* Sender side (Sender::gen_clues -> ClueKey::gen_clues, sender.rs:27-30, key_gen/clue.rs:27-34): `count` clues
  * under the clue public key (pa, pb) [512] u16 each, for global message indices index0.., encrypting d_msgs[i][7] (values
  * mod 8; NULL = seven 0's as the reference does).  Randomness is a counter hash of (seed, message index), see DESIGN.md.

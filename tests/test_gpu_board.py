@@ -56,6 +56,13 @@ def test_full_board_detect_pack_decode(detector, keypack, board):
     assert np.array_equal(slots[0], keypack.decrypt_decode(idx[0].cpu().numpy().view(np.uint64)).astype(np.uint16))
     found2, solved2 = ret.decode_digest(idx, pay, weights)
     assert found2 == list(planted) and np.array_equal(solved2, solved)
+    # ... and so does the C-ABI form (omr_decode_digest: bucket scan and mod-257 solver inside the library)
+    ret3 = omr.Retriever(detector, rp, z2n)
+    found3, solved3 = ret3.decode_digest_host(idx, pay, weights)
+    assert found3 == list(planted) and np.array_equal(solved3, solved)
+    singular = weights.copy(); singular[:, planted[1]] = singular[:, planted[0]]       # two equal columns: no unique solution
+    with pytest.raises(omr.InvertibleMatrix):                                          # OmrError::InvertibleMatrix (error.rs:4-8)
+        omr.Retriever(detector, rp, z2n).decode_digest_host(idx, pay, singular)
     # bit-exact against the oracle on a sample: 4 pertinent + 4 random messages
     sample = np.concatenate([planted[:4], np.array([0, 1, 31337, D - 1])])
     ref = keypack.detect(a[sample], b[sample], threads=8)

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include <mutex>
 
@@ -729,6 +730,115 @@ int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, co
                                          ctx->s_digest, ctx->stream))) return st;
     CK(cudaMemcpyAsync(out, ctx->s_digest, (size_t)n_cipher * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return OMR_OK;
+}
+
+// ---- recipient side, host-buffer form (Retriever::decode_digest, retriever.rs:188-260) -------------------------------------
+namespace {
+// solve_matrix_mod_257 (matrix.rs:164-247): Gaussian elimination over Z_257 on (m [rows][cols], pl [rows][612]); first
+// non-zero pivot, row swap, normalise, eliminate below, back-substitute.  false = singular (OmrError::InvertibleMatrix).
+bool solve_mod_257(std::vector<u32>& m, std::vector<u32>& pl, size_t rows, size_t cols) {
+    constexpr u32 P = OUT_P; constexpr size_t W = PAYLOAD_LEN;
+    if (rows < cols) return false;
+    u32 inv[P]; inv[0] = 0; inv[1] = 1;
+    for (u32 v = 2; v < P; ++v) inv[v] = (P - (P / v) * inv[P % v] % P) % P;          // INV_MOD_257 (matrix.rs:28-41)
+    for (size_t i = 0; i < cols; ++i) {
+        size_t pick = i;
+        while (pick < rows && m[pick * cols + i] == 0) ++pick;
+        if (pick == rows) return false;                                               // matrix.rs:181-183
+        if (pick != i) {
+            for (size_t c = 0; c < cols; ++c) std::swap(m[i * cols + c], m[pick * cols + c]);
+            for (size_t c = 0; c < W; ++c) std::swap(pl[i * W + c], pl[pick * W + c]);
+        }
+        const u32 iv = inv[m[i * cols + i]];
+        if (iv != 1) {
+            for (size_t c = i; c < cols; ++c) m[i * cols + c] = m[i * cols + c] * iv % P;
+            for (size_t c = 0; c < W; ++c) pl[i * W + c] = pl[i * W + c] * iv % P;
+        }
+        if (i == cols - 1) break;
+        for (size_t r = i + 1; r < rows; ++r) {
+            const u32 f = m[r * cols + i];
+            if (!f) continue;
+            for (size_t c = i; c < cols; ++c) m[r * cols + c] = (m[r * cols + c] + (P - f) * m[i * cols + c]) % P;
+            for (size_t c = 0; c < W; ++c) pl[r * W + c] = (pl[r * W + c] + (P - f) * pl[i * W + c]) % P;
+        }
+    }
+    for (size_t ic = cols; ic-- > 1;)
+        for (size_t r = 0; r < ic; ++r) {
+            const u32 f = m[r * cols + ic];
+            if (!f) continue;
+            for (size_t c = 0; c < W; ++c) pl[r * W + c] = (pl[r * W + c] + (P - f) * pl[ic * W + c]) % P;
+            m[r * cols + ic] = 0;
+        }
+    return true;
+}
+}  // namespace
+
+int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* z2_ntt, const uint64_t* index_cts, uint32_t n_index_cts,
+                      const uint64_t* payload_cts, uint32_t n_payload_cts, const uint16_t* weights, size_t weight_stride,
+                      uint64_t* indices_out, uint32_t* n_found, uint16_t* payloads_out) {
+    if (!ctx || !rp || !z2_ntt || !index_cts || !payload_cts || !weights || !indices_out || !n_found || !payloads_out) {
+        ctx_fail(ctx, "decode_digest: null argument"); return OMR_ERR_INVALID;
+    }
+    *n_found = 0;
+    const size_t w = rp->slots_per_bucket, S = rp->slots_per_segment, cc = rp->combination_count, per = rp->cmb_count_per_cipher;
+    if (rp->polynomial_size != OMR_N2 || rp->index_modulus != OMR_P || w < 2 || S == 0 || S % w || S > OMR_N2 || per == 0 ||
+        per * OMR_PAYLOAD_LEN > OMR_N2 || (size_t)n_payload_cts * per < cc || weight_stride < rp->all_payloads_count) {
+        ctx_fail(ctx, "decode_digest: inconsistent retrieval parameters"); return OMR_ERR_INVALID;
+    }
+    const size_t n = (size_t)n_index_cts + n_payload_cts;
+    std::vector<uint16_t> slots(n * OMR_N2);
+    {   // decrypt + inverse NTT + exact-integer decode of every slot on the GPU
+        u64 *d_key = nullptr, *d_ct = nullptr; uint16_t* d_out = nullptr;
+        auto release = [&]() { cudaFree(d_key); cudaFree(d_ct); cudaFree(d_out); };
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_key, OMR_N2 * sizeof(u64));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_ct, n * OMR_PV_WORDS * sizeof(u64));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, n * OMR_N2 * sizeof(uint16_t));
+        if (e == cudaSuccess) e = cudaMemcpy(d_key, z2_ntt, OMR_N2 * sizeof(u64), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_ct, index_cts, (size_t)n_index_cts * OMR_PV_WORDS * sizeof(u64), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_ct + (size_t)n_index_cts * OMR_PV_WORDS, payload_cts, (size_t)n_payload_cts * OMR_PV_WORDS * sizeof(u64), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { release(); ctx_fail(ctx, std::string("decode_digest: ") + cudaGetErrorString(e)); return OMR_ERR_CUDA; }
+        int st = omr_decrypt_decode_device(ctx, d_key, d_ct, n, d_out, ctx->stream);
+        if (st == OMR_OK) {
+            e = cudaMemcpyAsync(slots.data(), d_out, slots.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { ctx_fail(ctx, std::string("decode_digest: ") + cudaGetErrorString(e)); st = OMR_ERR_CUDA; }
+        }
+        release();
+        if (st) return st;
+    }
+    // decode_pertinent_indices (retriever.rs:63-130): a bucket counts when its flag slot decodes to exactly 1; the index is the
+    // base-257 number in the other slots, most significant last; ciphertexts are consumed until the set is full (:200-204)
+    std::vector<uint64_t> found;
+    for (uint32_t c = 0; c < n_index_cts && found.size() != rp->pertinent_count; ++c) {
+        const uint16_t* dec = slots.data() + (size_t)c * OMR_N2;
+        for (size_t seg = 0; seg + S <= (size_t)OMR_N2; seg += S)
+            for (size_t bk = 0; bk + w <= S; bk += w) {
+                const uint16_t* bucket = dec + seg + bk;
+                if (bucket[w - 1] != 1) continue;
+                uint64_t idx = 0;
+                for (size_t k = w - 1; k-- > 0;) idx = idx * OMR_P + bucket[k];
+                if (std::find(found.begin(), found.end(), idx) == found.end()) found.push_back(idx);
+            }
+    }
+    std::sort(found.begin(), found.end());
+    if (found.size() > rp->pertinent_count) { ctx_fail(ctx, "decode_digest: more indices than pertinent_count"); return OMR_ERR_INVALID; }
+    *n_found = (uint32_t)found.size();
+    for (size_t i = 0; i < found.size(); ++i) indices_out[i] = found[i];
+    if (found.empty()) return OMR_OK;
+    for (uint64_t i : found)
+        if (i >= rp->all_payloads_count) { ctx_fail(ctx, "decode_digest: decoded index outside the board"); return OMR_ERR_INVALID; }
+    // combination matrix from the weights (retriever.rs:215-240) and the combined payloads (:318-362)
+    const size_t cols = found.size();
+    std::vector<u32> m(cc * cols), pl(cc * OMR_PAYLOAD_LEN);
+    for (size_t r = 0; r < cc; ++r) {
+        for (size_t k = 0; k < cols; ++k) m[r * cols + k] = weights[r * weight_stride + found[k]] % OMR_P;
+        const uint16_t* dec = slots.data() + ((size_t)n_index_cts + r / per) * OMR_N2 + (r % per) * OMR_PAYLOAD_LEN;
+        for (size_t k = 0; k < OMR_PAYLOAD_LEN; ++k) pl[r * OMR_PAYLOAD_LEN + k] = dec[k];
+    }
+    if (!solve_mod_257(m, pl, cc, cols)) { ctx_fail(ctx, "matrix is not invertible"); return OMR_ERR_INVALID; }   // error.rs:4-8
+    for (size_t i = 0; i < cols * OMR_PAYLOAD_LEN; ++i) payloads_out[i] = (uint16_t)pl[i];
     return OMR_OK;
 }
 

@@ -60,6 +60,12 @@ def solve_matrix_mod_257(matrix, payloads):
     return pl[:cols].astype(np.uint16)
 
 
+def _to_host_u64(x):
+    if hasattr(x, "data_ptr"):
+        return x.cpu().numpy().view(np.uint64)
+    return np.asarray(x).view(np.uint64) if np.asarray(x).dtype != np.uint64 else np.asarray(x)
+
+
 class Retriever:
     """Retriever<F> (retriever.rs:26-61): holds the retrieval layout and the recipient's NTT-domain secret z2."""
 
@@ -107,6 +113,34 @@ class Retriever:
                 if r < rp.combination_count:
                     out[r] = dec[c, j * PAYLOAD_LENGTH:(j + 1) * PAYLOAD_LENGTH]
         return out
+
+    def decode_digest_host(self, encode_pertinent_indices, encode_pertinent_payloads, weights):
+        """decode_digest (retriever.rs:188-260) through the C ABI (omr_decode_digest): host arrays in, GPU decrypt/decode,
+        bucket scan and mod-257 solver in the library.  Returns (sorted indices, payloads [len(indices)][612]); raises
+        InvertibleMatrix when the combination matrix is singular."""
+        import ctypes as C
+        rp = self.params
+        idx = np.ascontiguousarray(_to_host_u64(encode_pertinent_indices)).reshape(-1, 2, N2)
+        pay = np.ascontiguousarray(_to_host_u64(encode_pertinent_payloads)).reshape(-1, 2, N2)
+        w = np.ascontiguousarray(weights, np.uint16)
+        if w.ndim != 2 or w.shape[0] < rp.combination_count:
+            raise OmrError(_lib.OMR_ERR_INVALID, "weights must be [combination_count][all_payloads_count]")
+        key = np.ascontiguousarray(self.key.cpu().numpy().view(np.uint64))
+        out_idx = np.zeros(max(1, rp.pertinent_count), np.uint64)
+        out_pay = np.zeros((max(1, rp.pertinent_count), PAYLOAD_LENGTH), np.uint16)
+        n_found = C.c_uint32(0)
+        rpc = rp.to_c()
+        det = self.detector
+        st = det.L.omr_decode_digest(det.h, C.byref(rpc), key.ctypes.data, idx.ctypes.data, idx.shape[0], pay.ctypes.data, pay.shape[0],
+                                     w.ctypes.data, w.shape[1], out_idx.ctypes.data, C.byref(n_found), out_pay.ctypes.data)
+        if st != _lib.OMR_OK:
+            msg = (det.L.omr_last_error(det.h) or b"").decode()
+            if "not invertible" in msg:
+                raise InvertibleMatrix()
+            raise OmrError(st, msg)
+        n = int(n_found.value)
+        self.pertinent_indices_set.update(int(v) for v in out_idx[:n])
+        return [int(v) for v in out_idx[:n]], out_pay[:n].copy()
 
     def decode_digest(self, encode_pertinent_indices, encode_pertinent_payloads, weights):
         """decode_digest (retriever.rs:188-260).  `weights` [combination_count (or more)][D] is the matrix the reference
