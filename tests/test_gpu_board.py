@@ -178,6 +178,33 @@ def test_determinism_and_scheduling_independence():
     assert np.array_equal(ref[pick].cpu().numpy().view(np.uint64), want)
 
 
+def test_two_recipients_concurrently(detector, keypack, decoy):
+    """Multi-recipient serving: two contexts with different detection keys on the same GPU, driven from two
+    streams at once, give what each gives alone — one context per stream is the concurrency contract of the header."""
+    import torch
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from stage_times import random_detector
+    other = random_detector(seed=11)
+    a0, b0 = keypack.gen_clues(501, 1)
+    a, b = decoy.gen_clues(502, 40)
+    a[7], b[7] = a0[0], b0[0]
+    da, db = torch.from_numpy(a.view(np.int16)).cuda(), torch.from_numpy(b.view(np.int16)).cuda()
+    alone = [detector.detect((da, db)).tensor.clone(), other.detect((da, db)).tensor.clone()]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            r1 = detector.detect((da, db)).tensor
+        with torch.cuda.stream(s2):
+            r2 = other.detect((da, db)).tensor
+        torch.cuda.synchronize()
+        assert torch.equal(r1, alone[0]) and torch.equal(r2, alone[1])
+    d = keypack.decrypt_decode(alone[0][7].cpu().numpy().view(np.uint64))
+    assert d[0] == 1 and not d[1:].any()                       # the recipient's message is pertinent under the recipient's key only
+    assert not torch.equal(alone[0][7], alone[1][7])
+
+
 def test_streaming_running_digest_equals_one_shot(detector, board):
     """messages arrive in batches; the running digest (omr_digest_add_mod) equals packing the whole board"""
     import torch
