@@ -153,6 +153,13 @@ int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64
                       const uint16_t* weights, size_t weight_stride,
                       uint64_t* indices_out, uint32_t* n_found, uint16_t* payloads_out);
 
+/* The combination weights exactly as the reference draws them (detector.rs:376-387, regenerated by the recipient at
+ * retriever.rs:215-226): StdRng::from_seed(seed32) (rand 0.8: ChaCha12) feeding Uniform::<u16>::new(0, 257), `count` draws in
+ * stream order into d_out (row-major [combination_count][all_payloads_count] when count is their product).  With this the
+ * 32-byte seed of the reference's API is all that crosses the boundary.  flags bit 0: generate strictly in order on one
+ * thread (the path taken when a draw is rejected, probability 2^-32 per draw; exposed for the tests). */
+int omr_weights_from_seed_device(omr_ctx* ctx, const uint8_t* seed32, size_t count, uint16_t* d_out, uint32_t flags, void* stream);
+
 /* Sender side (Sender::gen_clues -> ClueKey::gen_clues, sender.rs:27-30, key_gen/clue.rs:27-34): `count` clues
  * under the clue public key (pa, pb) [512] u16 each, for global message indices index0.., encrypting d_msgs[i][7] (values
  * mod 8; NULL = seven 0's as the reference does).  Randomness is a counter hash of (seed, message index), see DESIGN.md.

@@ -60,6 +60,11 @@ def test_full_board_detect_pack_decode(detector, keypack, board):
     ret3 = omr.Retriever(detector, rp, z2n)
     found3, solved3 = ret3.decode_digest_host(idx, pay, weights)
     assert found3 == list(planted) and np.array_equal(solved3, solved)
+    # the reference's own calling convention: only the 32-byte seed crosses the boundary on both sides
+    pay_seeded = detector.encode_pertinent_payloads(pv, payloads, rp.combination_count, 2, seed=bytes(range(32)), all_payloads_count=D)
+    assert torch.equal(pay_seeded, pay)
+    found4, solved4 = omr.Retriever(detector, rp, z2n).decode_digest_host(idx, pay_seeded, seed=bytes(range(32)))
+    assert found4 == list(planted) and np.array_equal(solved4, solved)
     singular = weights.copy(); singular[:, planted[1]] = singular[:, planted[0]]       # two equal columns: no unique solution
     with pytest.raises(omr.InvertibleMatrix):                                          # OmrError::InvertibleMatrix (error.rs:4-8)
         omr.Retriever(detector, rp, z2n).decode_digest_host(idx, pay, singular)

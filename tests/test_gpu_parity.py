@@ -144,6 +144,23 @@ def test_extreme_inputs_bit_exact(detector, keypack, shape):
     assert np.array_equal(tr.cpu().numpy().view(np.uint64), keypack.trace(ref_l2))
 
 
+def test_weights_from_seed_match_reference_stream(detector):
+    """detector.rs:376-387 / retriever.rs:215-226: the combination weights are StdRng::from_seed(seed) + Uniform(0, 257); the
+    GPU stream equals the oracle's restatement of rand 0.8 / rand_chacha 0.3 for ragged lengths around the 16-word ChaCha
+    block, for a board-sized matrix, and on the strictly in-order path that a rejected draw would take."""
+    import torch
+    for seed, rows, cols in ((bytes(range(32)), 1, 1), (bytes(range(32)), 1, 15), (bytes(32), 1, 17), (bytes([7] * 32), 3, 1000),
+                             (bytes(range(1, 33)), 55, 4096)):
+        ref = O.chacha12_weights(seed, rows * cols).reshape(rows, cols)
+        got = detector.weights_from_seed(seed, rows, cols); torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy().view(np.uint16), ref)
+        assert ref.max() < 257
+    ordered = detector.weights_from_seed(bytes([7] * 32), 3, 1000, in_order=True); torch.cuda.synchronize()
+    assert np.array_equal(ordered.cpu().numpy().view(np.uint16), O.chacha12_weights(bytes([7] * 32), 3000).reshape(3, 1000))
+    with pytest.raises(Exception):
+        detector.weights_from_seed(b"short", 1, 1)
+
+
 def test_omd_acceptance(detector, keypack, decoy):
     """omr_core/examples/omd.rs:45-58: pertinent -> [1,0,...,0], non-pertinent -> all 0."""
     a, b = _mixed_clues(keypack, decoy, 2, [0], seed=21)

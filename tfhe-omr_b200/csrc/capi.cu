@@ -63,6 +63,7 @@ struct omr_ctx {
     size_t cap = 0; u32* s_rlwe1 = nullptr; u32* s_lwe2 = nullptr; unsigned short *s_ca = nullptr, *s_cb = nullptr;
     size_t cap7 = 0; u32* s_rlwe7 = nullptr;      // per-(message, clue) accumulators of the L1 kernel
     int l2c_max_clusters = 0;                     // co-resident 6-CTA clusters (cudaOccupancyMaxActiveClusters)
+    int* d_flag = nullptr;                        // "a weight draw was rejected" flag of omr_weights_from_seed_device
     double* l2c_scratch = nullptr;                // partial sums exchanged inside a level-2 cluster
     unsigned long long* ks_part = nullptr;        // [KS_SPLIT_MAXB][KSK_PAD] partial sums of the split key switch
     // packing scratch
@@ -497,7 +498,7 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
-                    ctx->ks_part, ctx->l2c_scratch, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
+                    ctx->ks_part, ctx->l2c_scratch, ctx->d_flag, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) { if (ctx->p_rlwe7[k]) cudaFree(ctx->p_rlwe7[k]); if (ctx->p_rlwe1[k]) cudaFree(ctx->p_rlwe1[k]); if (ctx->p_lwe2[k]) cudaFree(ctx->p_lwe2[k]); }
     for (auto& ev : ctx->pev) if (ev) cudaEventDestroy(ev);
@@ -643,6 +644,22 @@ int omr_decrypt_decode_device(omr_ctx* ctx, const uint64_t* d_z2_ntt, const uint
     ++ctx->launches; CK(cudaGetLastError());
     decode_round_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ctx->s_partial, d_out, total);
     ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
+int omr_weights_from_seed_device(omr_ctx* ctx, const uint8_t* seed32, size_t count, uint16_t* d_out, uint32_t flags, void* stream) {
+    if (!ctx || (count && (!seed32 || !d_out))) { ctx_fail(ctx, "weights_from_seed: null argument"); return OMR_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    if (!count) return OMR_OK;
+    if (!ctx->d_flag) CK(cudaMalloc((void**)&ctx->d_flag, sizeof(int)));
+    ChaChaKey key;
+    for (int i = 0; i < 8; ++i) key.k[i] = (u32)seed32[4 * i] | ((u32)seed32[4 * i + 1] << 8) | ((u32)seed32[4 * i + 2] << 16) | ((u32)seed32[4 * i + 3] << 24);
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    const size_t blocks = (count + 15) / 16;
+    weights_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, s>>>(key, count, d_out, ctx->d_flag);
+    weights_serial_kernel<<<1, 1, 0, s>>>(key, count, d_out, ctx->d_flag, (int)(flags & 1u));
+    ctx->launches += 2; CK(cudaGetLastError());
     return OMR_OK;
 }
 

@@ -929,6 +929,58 @@ clue_gen_kernel(const unsigned short* __restrict__ pa, const unsigned short* __r
     }
 }
 
+// ---- combination weights from the reference's 32-byte seed ------------------------------------------------------------------
+// detector.rs:376-387 / retriever.rs:215-226: StdRng::from_seed(seed) (rand 0.8: ChaCha12, 64-bit block counter from 0, stream
+// 0) drives Uniform::<u16>::new(0, 257).sample_iter: one u32 per draw, v * 257 = hi:lo, accept when lo <= zone (zone = 2^32 - 2:
+// one u32 value in 2^32 is rejected), weight = hi.  One thread per 64-byte ChaCha block = 16 draws.  A rejection shifts every
+// later draw, so the parallel kernel only flags it and weights_serial_kernel then regenerates the whole stream in order.
+struct ChaChaKey { u32 k[8]; };
+__device__ __forceinline__ void chacha12_block(const ChaChaKey& key, u64 counter, u32 (&out)[16]) {
+    const u32 st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3],
+                        key.k[4], key.k[5], key.k[6], key.k[7], (u32)counter, (u32)(counter >> 32), 0u, 0u};
+    u32 x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = st[i];
+#define OMR_QR(a, b, c, d)                                                                                                        \
+    x[a] += x[b]; x[d] = __funnelshift_l(x[d] ^ x[a], x[d] ^ x[a], 16); x[c] += x[d]; x[b] = __funnelshift_l(x[b] ^ x[c], x[b] ^ x[c], 12); \
+    x[a] += x[b]; x[d] = __funnelshift_l(x[d] ^ x[a], x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = __funnelshift_l(x[b] ^ x[c], x[b] ^ x[c], 7);
+#pragma unroll
+    for (int r = 0; r < 12; r += 2) {
+        OMR_QR(0, 4, 8, 12) OMR_QR(1, 5, 9, 13) OMR_QR(2, 6, 10, 14) OMR_QR(3, 7, 11, 15)
+        OMR_QR(0, 5, 10, 15) OMR_QR(1, 6, 11, 12) OMR_QR(2, 7, 8, 13) OMR_QR(3, 4, 9, 14)
+    }
+#undef OMR_QR
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = x[i] + st[i];
+}
+constexpr u32 WEIGHT_ZONE = 0xFFFFFFFFu - (u32)((0xFFFFFFFFull - OUT_P + 1) % OUT_P);
+
+__global__ void weights_kernel(ChaChaKey key, size_t count, unsigned short* __restrict__ out, int* __restrict__ rejected) {
+    const size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk * 16 >= count) return;
+    u32 w[16];
+    chacha12_block(key, blk, w);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const u64 m = (u64)w[j] * OUT_P;
+        if ((u32)m > WEIGHT_ZONE) atomicExch(rejected, 1);
+        if (blk * 16 + j < count) out[blk * 16 + j] = (unsigned short)(m >> 32);
+    }
+}
+// exact in-order regeneration; runs only when weights_kernel saw a rejected draw (or on request, for the tests)
+__global__ void weights_serial_kernel(ChaChaKey key, size_t count, unsigned short* __restrict__ out, const int* __restrict__ rejected, int force) {
+    if (!force && !*rejected) return;
+    size_t n = 0;
+    for (u64 blk = 0; n < count; ++blk) {
+        u32 w[16];
+        chacha12_block(key, blk, w);
+        for (int j = 0; j < 16 && n < count; ++j) {
+            const u64 m = (u64)w[j] * OUT_P;
+            if ((u32)m <= WEIGHT_ZONE) out[n++] = (unsigned short)(m >> 32);
+        }
+    }
+}
+
 // ---- standalone batched NTTs (key upload in coefficient form, tests, API completeness) -----------------------------
 template <class F> struct GeoOf;
 template <> struct GeoOf<F1> { typedef GeoL1 G; };

@@ -133,6 +133,17 @@ class Detector:
     def launch_count(self):
         return int(self.L.omr_launch_count(self.h))
 
+    def weights_from_seed(self, seed, rows, cols, in_order=False):
+        """The reference's combination weights (detector.rs:376-387): StdRng::from_seed(seed) + Uniform(0, 257), rows x cols
+        draws in stream order, generated on the GPU (omr_weights_from_seed_device).  Returns a CUDA int16 tensor."""
+        torch = _torch()
+        seed = bytes(seed)
+        if len(seed) != 32:
+            raise OmrError(_lib.OMR_ERR_INVALID, "the seed is 32 bytes")
+        out = torch.empty((rows, cols), dtype=torch.int16, device=f"cuda:{self.device}")
+        self._ck(self.L.omr_weights_from_seed_device(self.h, seed, rows * cols, out.data_ptr(), 1 if in_order else 0, self._stream()))
+        return out
+
     def set_latency_shapes(self, enable):
         """omr_set_latency_shapes: small batches use the latency launch shapes (default) or the throughput shapes."""
         self._ck(self.L.omr_set_latency_shapes(self.h, 1 if enable else 0))
@@ -191,14 +202,29 @@ class Detector:
                                                   cipher_index, n_cipher, out.data_ptr(), self._stream()))
         return out
 
-    def encode_pertinent_payloads(self, pertinency_vector, payloads, combination_count, cmb_count_per_cipher, weights, out=None):
+    def seeded_weights(self, seed, combination_count, cmb_count_per_cipher, all_payloads_count):
+        """[ceil(cc / per) * per][D] weight matrix of the reference for a 32-byte seed: the first combination_count rows are
+        the ChaCha12 stream (weights_from_seed), the unused tail rows stay zero (detector.rs:370-371)."""
+        torch = _torch()
+        rows = -(-combination_count // cmb_count_per_cipher) * cmb_count_per_cipher
+        w = torch.zeros((rows, all_payloads_count), dtype=torch.int16, device=f"cuda:{self.device}")
+        w[:combination_count] = self.weights_from_seed(seed, combination_count, all_payloads_count)
+        return w
+
+    def encode_pertinent_payloads(self, pertinency_vector, payloads, combination_count, cmb_count_per_cipher, weights=None, out=None,
+                                  seed=None, all_payloads_count=None):
         """encode_pertinent_payloads (detector.rs:341-453).  payloads [count][612] u16, weights [rows][D] u16 with
         rows >= ceil(combination_count / cmb_count_per_cipher) * cmb_count_per_cipher (unused tail rows zero,
-        detector.rs:370-371), column = global message index.  numpy or CUDA tensors."""
+        detector.rs:370-371), column = global message index.  numpy or CUDA tensors.  Instead of `weights`, the reference's
+        32-byte `seed` (the StdRng the reference passes in) and the board size `all_payloads_count` may be given."""
         torch = _torch()
         pv = pertinency_vector
         dev = pv.tensor.device
         n_cipher = -(-combination_count // cmb_count_per_cipher)
+        if weights is None:
+            if seed is None or all_payloads_count is None:
+                raise OmrError(_lib.OMR_ERR_INVALID, "either weights or (seed, all_payloads_count) is required")
+            weights = self.seeded_weights(seed, combination_count, cmb_count_per_cipher, all_payloads_count)
         if not hasattr(payloads, "data_ptr"):
             payloads = torch.from_numpy(np.ascontiguousarray(payloads, np.uint16).reshape(-1, PAYLOAD_LENGTH).view(np.int16)).to(dev)
         if not hasattr(weights, "data_ptr"):

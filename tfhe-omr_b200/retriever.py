@@ -114,7 +114,15 @@ class Retriever:
                     out[r] = dec[c, j * PAYLOAD_LENGTH:(j + 1) * PAYLOAD_LENGTH]
         return out
 
-    def decode_digest_host(self, encode_pertinent_indices, encode_pertinent_payloads, weights):
+    def _weights(self, weights, seed):
+        if weights is not None:
+            return weights
+        if seed is None:
+            raise OmrError(_lib.OMR_ERR_INVALID, "either weights or the 32-byte seed is required")
+        rp = self.params                                     # regenerate the matrix from the seed (retriever.rs:215-226)
+        return self.detector.weights_from_seed(seed, rp.combination_count, rp.all_payloads_count).cpu().numpy().view(np.uint16)
+
+    def decode_digest_host(self, encode_pertinent_indices, encode_pertinent_payloads, weights=None, seed=None):
         """decode_digest (retriever.rs:188-260) through the C ABI (omr_decode_digest): host arrays in, GPU decrypt/decode,
         bucket scan and mod-257 solver in the library.  Returns (sorted indices, payloads [len(indices)][612]); raises
         InvertibleMatrix when the combination matrix is singular."""
@@ -122,7 +130,7 @@ class Retriever:
         rp = self.params
         idx = np.ascontiguousarray(_to_host_u64(encode_pertinent_indices)).reshape(-1, 2, N2)
         pay = np.ascontiguousarray(_to_host_u64(encode_pertinent_payloads)).reshape(-1, 2, N2)
-        w = np.ascontiguousarray(weights, np.uint16)
+        w = np.ascontiguousarray(self._weights(weights, seed), np.uint16)
         if w.ndim != 2 or w.shape[0] < rp.combination_count:
             raise OmrError(_lib.OMR_ERR_INVALID, "weights must be [combination_count][all_payloads_count]")
         key = np.ascontiguousarray(self.key.cpu().numpy().view(np.uint64))
@@ -142,11 +150,12 @@ class Retriever:
         self.pertinent_indices_set.update(int(v) for v in out_idx[:n])
         return [int(v) for v in out_idx[:n]], out_pay[:n].copy()
 
-    def decode_digest(self, encode_pertinent_indices, encode_pertinent_payloads, weights):
+    def decode_digest(self, encode_pertinent_indices, encode_pertinent_payloads, weights=None, seed=None):
         """decode_digest (retriever.rs:188-260).  `weights` [combination_count (or more)][D] is the matrix the reference
-        regenerates from the 32-byte seed (retriever.rs:215-226); it is passed explicitly.
+        regenerates from the 32-byte seed (retriever.rs:215-226); pass either the matrix or the `seed` itself.
         Returns (sorted indices, payloads [len(indices)][612]); raises InvertibleMatrix."""
         rp = self.params
+        weights = self._weights(weights, seed)
         for ct in encode_pertinent_indices:                              # ciphertexts are consumed until the set is full (:200-204)
             if self.decode_pertinent_indices(ct[None] if ct.ndim == 2 else ct):
                 break
