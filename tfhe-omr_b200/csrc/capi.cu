@@ -94,6 +94,7 @@ template <class T> int dalloc(omr_ctx* ctx, T** p, size_t n) {
 int ensure_scratch(omr_ctx* ctx, size_t B) {
     if (B <= ctx->cap) return OMR_OK;
     cudaFree(ctx->s_rlwe1); cudaFree(ctx->s_lwe2); cudaFree(ctx->s_ca); cudaFree(ctx->s_cb);
+    ctx->s_rlwe1 = nullptr; ctx->s_lwe2 = nullptr; ctx->s_ca = nullptr; ctx->s_cb = nullptr;      // a failed re-allocation must not leave stale pointers
     ctx->cap = 0;
     int st;
     if ((st = dalloc(ctx, &ctx->s_rlwe1, B * 2 * F1::N))) return st;
@@ -307,7 +308,7 @@ int detect_device(omr_ctx* ctx, const unsigned short* d_ca, const unsigned short
 
 int ensure_partial(omr_ctx* ctx, size_t words) {
     if (words <= ctx->partial_words) return OMR_OK;
-    cudaFree(ctx->s_partial); ctx->partial_words = 0;
+    cudaFree(ctx->s_partial); ctx->s_partial = nullptr; ctx->partial_words = 0;
     int st; if ((st = dalloc(ctx, &ctx->s_partial, words))) return st;
     ctx->partial_words = words;
     return OMR_OK;
@@ -333,7 +334,7 @@ int pack_device(omr_ctx* ctx, bool indices, const u64* d_pv, size_t count, u64 i
 
 int ensure_digest(omr_ctx* ctx, size_t words) {
     if (words <= ctx->digest_words) return OMR_OK;
-    cudaFree(ctx->s_digest); ctx->digest_words = 0;
+    cudaFree(ctx->s_digest); ctx->s_digest = nullptr; ctx->digest_words = 0;
     int st; if ((st = dalloc(ctx, &ctx->s_digest, words))) return st;
     ctx->digest_words = words;
     return OMR_OK;
@@ -738,8 +739,8 @@ int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, co
         if (count != ctx->pv_count) { ctx_fail(ctx, "encode_payloads: payload count != pertinency store size"); return OMR_ERR_INVALID; }
         if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
         const size_t pe = count * OMR_PAYLOAD_LEN, we = (size_t)n_cipher * cmb_per_cipher * weight_stride;
-        if (pe > ctx->payload_elems) { cudaFree(ctx->s_payloads); ctx->payload_elems = 0; if ((st = dalloc(ctx, &ctx->s_payloads, pe))) return st; ctx->payload_elems = pe; }
-        if (we > ctx->weight_elems) { cudaFree(ctx->s_weights); ctx->weight_elems = 0; if ((st = dalloc(ctx, &ctx->s_weights, we))) return st; ctx->weight_elems = we; }
+        if (pe > ctx->payload_elems) { cudaFree(ctx->s_payloads); ctx->s_payloads = nullptr; ctx->payload_elems = 0; if ((st = dalloc(ctx, &ctx->s_payloads, pe))) return st; ctx->payload_elems = pe; }
+        if (we > ctx->weight_elems) { cudaFree(ctx->s_weights); ctx->s_weights = nullptr; ctx->weight_elems = 0; if ((st = dalloc(ctx, &ctx->s_weights, we))) return st; ctx->weight_elems = we; }
         CK(cudaMemcpyAsync(ctx->s_payloads, payloads, pe * 2, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->s_weights, weights, we * 2, cudaMemcpyHostToDevice, ctx->stream));
     }
