@@ -160,6 +160,12 @@ int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64
  * thread (the path taken when a draw is rejected, probability 2^-32 per draw; exposed for the tests). */
 int omr_weights_from_seed_device(omr_ctx* ctx, const uint8_t* seed32, size_t count, uint16_t* d_out, uint32_t flags, void* stream);
 
+/* omr_encode_payloads with the reference's own argument — the seed of the rng it is handed (detector.rs:341, 376-387) —
+ * instead of a weight matrix: weights are generated on the GPU (omr_weights_from_seed_device), rows beyond combination_count
+ * are zero.  out [ceil(combination_count / cmb_per_cipher)][2][2048]. */
+int omr_encode_payloads_seeded(omr_ctx* ctx, const uint16_t* payloads, size_t count, const uint8_t* seed32, uint64_t all_payloads_count,
+                               uint32_t combination_count, uint32_t cmb_per_cipher, uint64_t* out);
+
 /* Sender side (Sender::gen_clues -> ClueKey::gen_clues, sender.rs:27-30, key_gen/clue.rs:27-34): `count` clues
  * under the clue public key (pa, pb) [512] u16 each, for global message indices index0.., encrypting d_msgs[i][7] (values
  * mod 8; NULL = seven 0's as the reference does).  Randomness is a counter hash of (seed, message index), see DESIGN.md.

@@ -115,6 +115,10 @@ def test_host_buffer_api_matches_device_api(detector, board):
     ph = detector.encode_payloads_host(payloads[:n], weights, rp.combination_count, 2)
     assert np.array_equal(ih, detector.encode_pertinent_indices(rp, dev, seed=5, cipher_index=1, n_cipher=2).cpu().numpy().view(np.uint64))
     assert np.array_equal(ph, detector.encode_pertinent_payloads(dev, payloads[:n], rp.combination_count, 2, weights).cpu().numpy().view(np.uint64))
+    seed = bytes(range(100, 132))                                             # the reference's calling convention: rng seed, not weights
+    ps = detector.encode_payloads_seeded_host(payloads[:n], seed, D, rp.combination_count, 2)
+    assert np.array_equal(ps, detector.encode_pertinent_payloads(dev, payloads[:n], rp.combination_count, 2, seed=seed,
+                                                                 all_payloads_count=D).cpu().numpy().view(np.uint64))
     with pytest.raises(omr.OmrError):                                         # the store must stay contiguous
         detector.detect_host(a[:1], b[:1], global_index0=5)
     detector.pv_reset()

@@ -751,6 +751,32 @@ int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, co
     return OMR_OK;
 }
 
+// encode_pertinent_payloads with the reference's own argument: the rng seed instead of a weight matrix (detector.rs:341-453)
+int omr_encode_payloads_seeded(omr_ctx* ctx, const uint16_t* payloads, size_t count, const uint8_t* seed32, uint64_t all_payloads_count,
+                               uint32_t combination_count, uint32_t cmb_per_cipher, uint64_t* out) {
+    if (!ctx || !out || !payloads || !seed32 || !cmb_per_cipher || !combination_count) { ctx_fail(ctx, "encode_payloads_seeded: bad argument"); return OMR_ERR_INVALID; }
+    const uint32_t n_cipher = (combination_count + cmb_per_cipher - 1) / cmb_per_cipher;
+    const size_t rows = (size_t)n_cipher * cmb_per_cipher, we = rows * all_payloads_count, pe = count * OMR_PAYLOAD_LEN;
+    int st;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+        if (!ctx->pv_any) { ctx_fail(ctx, "encode_payloads: empty pertinency store"); return OMR_ERR_STATE; }
+        if (count != ctx->pv_count) { ctx_fail(ctx, "encode_payloads: payload count != pertinency store size"); return OMR_ERR_INVALID; }
+        if (ctx->pv_index0 + count > all_payloads_count) { ctx_fail(ctx, "encode_payloads: store exceeds all_payloads_count"); return OMR_ERR_INVALID; }
+        if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
+        if (pe > ctx->payload_elems) { cudaFree(ctx->s_payloads); ctx->s_payloads = nullptr; ctx->payload_elems = 0; if ((st = dalloc(ctx, &ctx->s_payloads, pe))) return st; ctx->payload_elems = pe; }
+        if (we > ctx->weight_elems) { cudaFree(ctx->s_weights); ctx->s_weights = nullptr; ctx->weight_elems = 0; if ((st = dalloc(ctx, &ctx->s_weights, we))) return st; ctx->weight_elems = we; }
+        CK(cudaMemcpyAsync(ctx->s_payloads, payloads, pe * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->s_weights, 0, we * 2, ctx->stream));            // unused tail rows stay zero (detector.rs:370-371)
+    }
+    if ((st = omr_weights_from_seed_device(ctx, seed32, (size_t)combination_count * all_payloads_count, ctx->s_weights, 0, ctx->stream))) return st;
+    if ((st = omr_encode_payloads_device(ctx, ctx->pv, ctx->s_payloads, count, ctx->pv_index0, ctx->s_weights, all_payloads_count, n_cipher, cmb_per_cipher,
+                                         ctx->s_digest, ctx->stream))) return st;
+    CK(cudaMemcpyAsync(out, ctx->s_digest, (size_t)n_cipher * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return OMR_OK;
+}
+
 // ---- recipient side, host-buffer form (Retriever::decode_digest, retriever.rs:188-260) -------------------------------------
 namespace {
 // solve_matrix_mod_257 (matrix.rs:164-247): Gaussian elimination over Z_257 on (m [rows][cols], pl [rows][612]); first

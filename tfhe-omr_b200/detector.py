@@ -292,6 +292,14 @@ class Detector:
         self._ck(self.L.omr_encode_indices(self.h, C.byref(rp), seed, cipher_index, n_cipher, out.ctypes.data))
         return out
 
+    def encode_payloads_seeded_host(self, payloads, seed, all_payloads_count, combination_count, cmb_count_per_cipher):
+        payloads = np.ascontiguousarray(payloads, np.uint16).reshape(-1, PAYLOAD_LENGTH)
+        n_cipher = -(-combination_count // cmb_count_per_cipher)
+        out = np.empty((n_cipher, 2, N2), np.uint64)
+        self._ck(self.L.omr_encode_payloads_seeded(self.h, payloads.ctypes.data, payloads.shape[0], bytes(seed), all_payloads_count,
+                                                   combination_count, cmb_count_per_cipher, out.ctypes.data))
+        return out
+
     def encode_payloads_host(self, payloads, weights, combination_count, cmb_count_per_cipher):
         payloads = np.ascontiguousarray(payloads, np.uint16).reshape(-1, PAYLOAD_LENGTH); weights = np.ascontiguousarray(weights, np.uint16)
         n_cipher = -(-combination_count // cmb_count_per_cipher)
