@@ -308,7 +308,7 @@ def cpu_baseline(key_host, args, steps=1, native=True):
     except Exception:
         native = False
     cores = os.cpu_count() or 1
-    sample = max(2, min(args.cpu_sample, 2 * cores))
+    sample = max(2, min(args.cpu_sample, 4 * cores))          # ~10-30 s of CPU work: 3 messages per thread at ~0.4 s each
     kp = O.KeyPack(blobs=key_host, native=native)
     rng = np.random.default_rng(3)
     a = rng.integers(0, 2048, (sample, 512), dtype=np.uint16); b = rng.integers(0, 2048, (sample, 7), dtype=np.uint16)
@@ -345,7 +345,7 @@ def run_reference(args):
     except Exception:
         native = False
     cores = os.cpu_count() or 1
-    sample = max(2, min(args.cpu_sample, 2 * cores))
+    sample = max(2, min(args.cpu_sample, 4 * cores))          # ~10-30 s of CPU work: 3 messages per thread at ~0.4 s each
     kp = O.KeyPack(blobs=O.random_key_blobs(20261018), native=native)
     rng = np.random.default_rng(3)
     a = rng.integers(0, 2048, (sample, 512), dtype=np.uint16); b = rng.integers(0, 2048, (sample, 7), dtype=np.uint16)
@@ -390,7 +390,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--messages-per-step", type=int, default=8192)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=16)
+    ap.add_argument("--cpu-sample", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2-traffic-bytes", type=float, default=None, help="dram bytes per l2_blind_rotate launch from an ncu --set full capture")
     args = ap.parse_args()
