@@ -273,7 +273,7 @@ def run_ours(args):
                      "design_min_bytes": int(BSK2_BYTES * (-(-M // (2 * n_sm))) + M * (671 * 4 + 2 * 2048 * 8)),
                      "note": "compute bound (FP64 / integer issue), not HBM bound: see roofline_compute.  algorithmic = one pass over BSK2 per "
                              "launch; the accumulators live in shared memory (2 messages per SM), so this design re-streams BSK2 once per wave "
-                             "of 2 x n_sm messages (design_min_bytes); traffic / design_min = the re-reads caused by CTAs drifting apart"},
+                             "of 2 x n_sm messages (design_min_bytes); traffic / design_min ~ 2 is consistent with each of the two L2 partitions (dies) fetching its own copy"},
         "roofline_compute": {
             "bound": "fp64+int pipes", "achieved": round(1.0 / t_meas, 1), "peak": round(1.0 / t_roof, 1), "unit": "messages/s/GPU",
             "frac": round(t_roof / t_meas, 4),
