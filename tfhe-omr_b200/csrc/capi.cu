@@ -76,11 +76,7 @@ struct omr_ctx {
     uint64_t launches = 0;
     int n_sm = 148;
     bool latency_shapes = true;                   // omr_set_latency_shapes / OMR_LATENCY_SHAPES=0: throughput shapes for every batch size
-    bool l1_half = false;                         // L1 kernel shape for the stand-alone stage: <4, half tile> or <8, whole tile>
     // two-stream software pipeline of detect_device
-    bool overlap = false; size_t chunk = 1184;   // measured slower than the plain sequence: off unless OMR_OVERLAP=1
-    cudaStream_t sA = nullptr, sB = nullptr; cudaEvent_t pev[7] = {};
-    size_t pipe_cap = 0; u32* p_rlwe7[2] = {nullptr, nullptr}; u32* p_rlwe1[2] = {nullptr, nullptr}; u32* p_lwe2[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -120,10 +116,7 @@ int ensure_pv(omr_ctx* ctx, size_t need) {
 }
 
 // ---- launches -------------------------------------------------------------------------------------------------------
-constexpr size_t L1_HALF_EXCLUSIVE_SMEM = 120 * 1024;      // 2 x (120+1) KiB > 228 KiB per SM; (120+1) + (L2_SMEM+1) KiB fits
-static_assert(L1Cfg<4, true>::SMEM <= L1_HALF_EXCLUSIVE_SMEM && L1_HALF_EXCLUSIVE_SMEM + L2_SMEM + 2048 <= 228 * 1024, "co-residency budget");
-int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* rlwe7, u32* out, bool half, cudaStream_t s,
-                  bool exclusive_half = false);
+int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* rlwe7, u32* out, cudaStream_t s);
 int launch_l1(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* out, cudaStream_t s) {
     if (!B) return OMR_OK;
     if (B > ctx->cap7) {
@@ -131,7 +124,7 @@ int launch_l1(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, 
         CK(cudaMalloc((void**)&ctx->s_rlwe7, B * CLUE_COUNT * 2 * F1::N * sizeof(u32)));
         ctx->cap7 = B;
     }
-    return launch_l1_raw(ctx, ca, cb, B, ctx->s_rlwe7, out, ctx->l1_half, s);
+    return launch_l1_raw(ctx, ca, cb, B, ctx->s_rlwe7, out, s);
 }
 constexpr size_t KS_SPLIT_MAXB = 256;
 int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s) {
@@ -175,133 +168,54 @@ int launch_trace(omr_ctx* ctx, u64* ct, size_t B, cudaStream_t s) {
     return OMR_OK;
 }
 
-// L1 kernel into caller-provided per-clue buffer (no internal allocation), shape chosen by `half`
-int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* rlwe7, u32* out, bool half, cudaStream_t s,
-                  bool exclusive_half) {
+// L1 kernel into caller-provided per-clue buffer (no internal allocation); the shape follows the number of blind rotations
+int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* rlwe7, u32* out, cudaStream_t s) {
     const size_t n_clues = B * CLUE_COUNT;
-    // exclusive_half: pad the request so that two such CTAs cannot share an SM but one of them plus one L2 CTA can
-    const size_t smem_half = exclusive_half ? L1_HALF_EXCLUSIVE_SMEM : L1Cfg<4, true>::SMEM;
     // latency shape: with fewer blind rotations than SMs every rotation gets an SM of its own (8 groups share one rotation)
-    if (n_clues <= (size_t)ctx->n_sm && !half && ctx->latency_shapes)
+    if (n_clues <= (size_t)ctx->n_sm && ctx->latency_shapes)
         l1_blind_rotate_lat_kernel<<<(unsigned)n_clues, L1L_THREADS, L1L_SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, ctx->tb);
-    else if (half)
-        l1_blind_rotate_kernel<4, true><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4, true>::THREADS, smem_half, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     else if (n_clues <= 2 * (size_t)ctx->n_sm && ctx->latency_shapes)      // mid-size batches: fewer rotations per CTA, every SM busy
-        l1_blind_rotate_kernel<2, false><<<(unsigned)((n_clues + 1) / 2), L1Cfg<2, false>::THREADS, L1Cfg<2, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
+        l1_blind_rotate_kernel<2><<<(unsigned)((n_clues + 1) / 2), L1Cfg<2>::THREADS, L1Cfg<2>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     else if (n_clues <= 4 * (size_t)ctx->n_sm && ctx->latency_shapes)
-        l1_blind_rotate_kernel<4, false><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4, false>::THREADS, L1Cfg<4, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
+        l1_blind_rotate_kernel<4><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4>::THREADS, L1Cfg<4>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     else
-        l1_blind_rotate_kernel<8, false><<<(unsigned)((n_clues + 7) / 8), L1Cfg<8, false>::THREADS, L1Cfg<8, false>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
+        l1_blind_rotate_kernel<8><<<(unsigned)((n_clues + 7) / 8), L1Cfg<8>::THREADS, L1Cfg<8>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     ++ctx->launches; CK(cudaGetLastError());
     sum7_kernel<<<(unsigned)((B * 2 * F1::N + 255) / 256), 256, 0, s>>>(rlwe7, out, B);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
 
-int ensure_pipe(omr_ctx* ctx, size_t C) {
-    if (!ctx->sA) {
-        int lo = 0, hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&ctx->sA, cudaStreamNonBlocking, hi));       // integer-pipe side gets priority (see below)
-        CK(cudaStreamCreateWithPriority(&ctx->sB, cudaStreamNonBlocking, lo));
-        for (auto& e : ctx->pev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
-    if (C <= ctx->pipe_cap) return OMR_OK;
-    for (int k = 0; k < 2; ++k) { cudaFree(ctx->p_rlwe7[k]); cudaFree(ctx->p_rlwe1[k]); cudaFree(ctx->p_lwe2[k]); ctx->p_rlwe7[k] = nullptr; ctx->p_rlwe1[k] = nullptr; ctx->p_lwe2[k] = nullptr; }
-    ctx->pipe_cap = 0;
-    int st;
-    for (int k = 0; k < 2; ++k) {
-        if ((st = dalloc(ctx, &ctx->p_rlwe7[k], C * CLUE_COUNT * 2 * F1::N))) return st;
-        if ((st = dalloc(ctx, &ctx->p_rlwe1[k], C * 2 * F1::N))) return st;
-        if ((st = dalloc(ctx, &ctx->p_lwe2[k], C * LWE2_STRIDE_IN))) return st;
-    }
-    ctx->pipe_cap = C;
-    return OMR_OK;
-}
-
-// The whole per-message pipeline for a batch.  Large batches are cut into chunks and software-pipelined over two
-// streams: the integer-pipe side (L1 blind rotations, sum, key switch) of chunk j+1 runs concurrently with the
-// FP64-pipe side (L2 blind rotation) and the trace of chunk j.  The L1 kernel is launched in its half-SM shape
-// (l1_blind_rotate_kernel<4,true>: 112 KiB smem, 32 K registers) so that one L1 CTA and one L2 CTA are co-resident on an
-// SM and the integer and FP64 pipes are busy at the same time; the L1 stream has the higher priority so that a freed
-// half-SM is refilled by an L1 CTA whenever one is pending (an L2 CTA always fits the other half).
+// The whole per-message pipeline for a batch, stream-ordered on the caller's stream; batches beyond MAXB messages are cut
+// into chunks so that the scratch stays bounded.  (Running the integer level-1 side of one chunk concurrently with the FP64
+// level-2 side of the previous one was tried and is slower — DESIGN.md §4 — so there is exactly one stream.)
 int detect_device(omr_ctx* ctx, const unsigned short* d_ca, const unsigned short* d_cb, size_t B, u64* d_pv, cudaStream_t s,
                   omr_stage_times* times) {
     int st;
     if (times) *times = omr_stage_times{};
     if (!B) return OMR_OK;
-    const size_t C = ctx->chunk;
-    if (!ctx->overlap || B <= C) {                                 // plain sequence on the caller's stream, scratch bounded by MAXB
-        const size_t MAXB = 16384;
-        if ((st = ensure_scratch(ctx, B < MAXB ? B : MAXB))) return st;
-        for (size_t off = 0; off < B; off += MAXB) {
-            const size_t nb = B - off < MAXB ? B - off : MAXB;
-            u64* pv = d_pv + off * OMR_PV_WORDS;
-            if (times) CK(cudaEventRecord(ctx->ev[0], s));
-            if ((st = launch_l1(ctx, d_ca + off * CLUE_N, d_cb + off * CLUE_COUNT, nb, ctx->s_rlwe1, s))) return st;
-            if ((st = launch_ks(ctx, ctx->s_rlwe1, nb, ctx->s_lwe2, s))) return st;
-            if (times) CK(cudaEventRecord(ctx->ev[1], s));
-            if ((st = launch_l2(ctx, ctx->s_lwe2, nb, pv, s))) return st;
-            if (times) CK(cudaEventRecord(ctx->ev[2], s));
-            if ((st = launch_trace(ctx, pv, nb, s))) return st;
-            if (times) {
-                CK(cudaEventRecord(ctx->ev[3], s));
-                CK(cudaEventSynchronize(ctx->ev[3]));
-                float a = 0, b = 0, c = 0;
-                CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
-                CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
-                CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
-                times->first_level_bootstrapping_ms += a; times->second_level_bootstrapping_ms += b; times->trace_ms += c;
-                times->detect_ms += a + b + c;
-            }
-        }
-        return OMR_OK;
-    }
-    if ((st = ensure_pipe(ctx, C))) return st;
-    cudaStream_t sA = ctx->sA, sB = ctx->sB;
-    cudaEvent_t* pev = ctx->pev;                                    // 0 start, 1-2 evA[set], 3-4 evB[set], 5 endA, 6 endB
-    const size_t nchunks = (B + C - 1) / C;
-    std::vector<cudaEvent_t> tev;                                   // timing events: per chunk l1 begin/end, l2 begin/end, trace end
-    if (times) {
-        tev.resize(nchunks * 5);
-        for (auto& e : tev) CK(cudaEventCreate(&e));
-        CK(cudaEventRecord(ctx->ev[0], s));
-    }
-    CK(cudaEventRecord(pev[0], s));
-    CK(cudaStreamWaitEvent(sA, pev[0], 0)); CK(cudaStreamWaitEvent(sB, pev[0], 0));
-    for (size_t j = 0; j < nchunks; ++j) {
-        const size_t off = j * C, nb = B - off < C ? B - off : C;
-        const int set = (int)(j & 1);
-        if (times) CK(cudaEventRecord(tev[j * 5 + 0], sA));
-        if ((st = launch_l1_raw(ctx, d_ca + off * CLUE_N, d_cb + off * CLUE_COUNT, nb, ctx->p_rlwe7[set], ctx->p_rlwe1[set], true, sA, /*exclusive_half=*/j > 0))) return st;
-        if (j >= 2) CK(cudaStreamWaitEvent(sA, pev[3 + set], 0));   // lwe2[set] is still being read by L2 of chunk j-2
-        if ((st = launch_ks(ctx, ctx->p_rlwe1[set], nb, ctx->p_lwe2[set], sA))) return st;
-        if (times) CK(cudaEventRecord(tev[j * 5 + 1], sA));
-        CK(cudaEventRecord(pev[1 + set], sA));
-        CK(cudaStreamWaitEvent(sB, pev[1 + set], 0));
-        if (times) CK(cudaEventRecord(tev[j * 5 + 2], sB));
-        if ((st = launch_l2(ctx, ctx->p_lwe2[set], nb, d_pv + off * OMR_PV_WORDS, sB))) return st;
-        CK(cudaEventRecord(pev[3 + set], sB));
-        if (times) CK(cudaEventRecord(tev[j * 5 + 3], sB));
-        if ((st = launch_trace(ctx, d_pv + off * OMR_PV_WORDS, nb, sB))) return st;
-        if (times) CK(cudaEventRecord(tev[j * 5 + 4], sB));
-    }
-    CK(cudaEventRecord(pev[5], sA)); CK(cudaEventRecord(pev[6], sB));
-    CK(cudaStreamWaitEvent(s, pev[5], 0)); CK(cudaStreamWaitEvent(s, pev[6], 0));
-    if (times) {
-        CK(cudaEventRecord(ctx->ev[3], s));
-        CK(cudaEventSynchronize(ctx->ev[3]));
-        float tot = 0;
-        CK(cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[3]));
-        times->detect_ms = tot;                                    // wall time of the pipelined batch on the device
-        for (size_t j = 0; j < nchunks; ++j) {                     // stage times = kernel durations in situ (they overlap)
+    const size_t MAXB = 16384;
+    if ((st = ensure_scratch(ctx, B < MAXB ? B : MAXB))) return st;
+    for (size_t off = 0; off < B; off += MAXB) {
+        const size_t nb = B - off < MAXB ? B - off : MAXB;
+        u64* pv = d_pv + off * OMR_PV_WORDS;
+        if (times) CK(cudaEventRecord(ctx->ev[0], s));
+        if ((st = launch_l1(ctx, d_ca + off * CLUE_N, d_cb + off * CLUE_COUNT, nb, ctx->s_rlwe1, s))) return st;
+        if ((st = launch_ks(ctx, ctx->s_rlwe1, nb, ctx->s_lwe2, s))) return st;
+        if (times) CK(cudaEventRecord(ctx->ev[1], s));
+        if ((st = launch_l2(ctx, ctx->s_lwe2, nb, pv, s))) return st;
+        if (times) CK(cudaEventRecord(ctx->ev[2], s));
+        if ((st = launch_trace(ctx, pv, nb, s))) return st;
+        if (times) {
+            CK(cudaEventRecord(ctx->ev[3], s));
+            CK(cudaEventSynchronize(ctx->ev[3]));
             float a = 0, b = 0, c = 0;
-            CK(cudaEventElapsedTime(&a, tev[j * 5 + 0], tev[j * 5 + 1]));
-            CK(cudaEventElapsedTime(&b, tev[j * 5 + 2], tev[j * 5 + 3]));
-            CK(cudaEventElapsedTime(&c, tev[j * 5 + 3], tev[j * 5 + 4]));
+            CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+            CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+            CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
             times->first_level_bootstrapping_ms += a; times->second_level_bootstrapping_ms += b; times->trace_ms += c;
+            times->detect_ms += a + b + c;
         }
-        for (auto& e : tev) cudaEventDestroy(e);
     }
     return OMR_OK;
 }
@@ -417,25 +331,20 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         CKC(cudaMemcpyToSymbol(c_tw1_head, h1, sizeof h1));
         CKC(cudaMemcpyToSymbol(c_tw2d_head, h2, sizeof h2));
     }
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<8, false>::SMEM));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<8>::SMEM));
     CKC(cudaFuncSetAttribute(l1_blind_rotate_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1L_SMEM));
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<2, false>::SMEM));
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<4, false>::SMEM));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<2>::SMEM));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<4>::SMEM));
     { cudaDeviceProp prop; CKC(cudaGetDeviceProperties(&prop, device)); ctx->n_sm = prop.multiProcessorCount; }
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1_HALF_EXCLUSIVE_SMEM));
     // always carve out the maximum shared memory for the big kernels: with the driver's default heuristic an occasional
     // launch of l2_blind_rotate_kernel got a smaller carve-out and ran at 1 CTA/SM (278 ms instead of 215 ms for 2 368 messages)
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(keyswitch_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(pack_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(pack_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    ctx->l1_half = getenv("OMR_L1_HALF") != nullptr;
-    if (const char* e = getenv("OMR_OVERLAP")) ctx->overlap = atoi(e) != 0;
     if (const char* e = getenv("OMR_LATENCY_SHAPES")) ctx->latency_shapes = atoi(e) != 0;
-    if (const char* e = getenv("OMR_CHUNK")) { long v = atol(e); if (v >= 8) ctx->chunk = (size_t)v; }
     CKC(cudaFuncSetAttribute(keyswitch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
     CKC(cudaFuncSetAttribute(keyswitch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
     CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L2_SMEM));
@@ -501,10 +410,6 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
                     ctx->ks_part, ctx->l2c_scratch, ctx->d_flag, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (int k = 0; k < 2; ++k) { if (ctx->p_rlwe7[k]) cudaFree(ctx->p_rlwe7[k]); if (ctx->p_rlwe1[k]) cudaFree(ctx->p_rlwe1[k]); if (ctx->p_lwe2[k]) cudaFree(ctx->p_lwe2[k]); }
-    for (auto& ev : ctx->pev) if (ev) cudaEventDestroy(ev);
-    if (ctx->sA) cudaStreamDestroy(ctx->sA);
-    if (ctx->sB) cudaStreamDestroy(ctx->sB);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

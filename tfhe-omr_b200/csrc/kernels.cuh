@@ -128,28 +128,26 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, u32 bytes, 
 constexpr int L1_GROUP = GeoL1::NT;                        // 64
 constexpr int L1_TILE_WORDS = 2 * G1::LEVELS * 2 * F1::N;  // 16384 u32 = 64 KiB
 constexpr int L1_GROUP_WORDS = 2 * F1::N + 2 * GeoL1::BUF;
-// Two shapes of the same kernel:
-//   <8, false>  512 threads, whole 64 KiB tile per step      — one CTA fills an SM (stand-alone stage)
-//   <4, true>   256 threads, the tile in two 32 KiB halves   — half an SM (112 KiB, 32 K registers), so that one such CTA and
-//               one l2_blind_rotate CTA (FP64 pipe) are co-resident and the integer and FP64 pipes run concurrently.
-template <int SLOTS, bool HALF> struct L1Cfg {
+// SLOTS = blind rotations per CTA: 8 fills an SM (512 threads); 4 and 2 serve mid-size batches that could not give every
+// SM an 8-rotation CTA (capi.cu: launch_l1_raw).
+template <int SLOTS> struct L1Cfg {
     static constexpr int THREADS = SLOTS * L1_GROUP;
-    static constexpr int TILE_WORDS = HALF ? L1_TILE_WORDS / 2 : L1_TILE_WORDS;
-    static constexpr size_t SMEM = (size_t)TILE_WORDS * 4 + (HALF ? 1 : 2) * F1::N * sizeof(uint2) + (size_t)SLOTS * L1_GROUP_WORDS * 4 +
+    static constexpr int TILE_WORDS = L1_TILE_WORDS;
+    static constexpr size_t SMEM = (size_t)TILE_WORDS * 4 + 2 * F1::N * sizeof(uint2) + (size_t)SLOTS * L1_GROUP_WORDS * 4 +
                                    (size_t)SLOTS * CLUE_N * sizeof(unsigned short) + 16;
 };
 
-template <int SLOTS, bool HALF>
-__global__ void __launch_bounds__(SLOTS * L1_GROUP, HALF ? 2 : 1)
+template <int SLOTS>
+__global__ void __launch_bounds__(SLOTS * L1_GROUP, 1)
 l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned short* __restrict__ clue_b,
                        const u32* __restrict__ bsk1, u32* __restrict__ out /*[n_clues][2][N]*/, int n_clues, Tables tb) {
-    typedef F1 F; typedef G1 G; typedef GeoL1 GEO; typedef ArInt<F1> AR; typedef L1Cfg<SLOTS, HALF> CFG;
+    typedef F1 F; typedef G1 G; typedef GeoL1 GEO; typedef ArInt<F1> AR; typedef L1Cfg<SLOTS> CFG;
     constexpr int N = F::N, E = GEO::E, L = G::LEVELS, THREADS = CFG::THREADS;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     u32* ktile = reinterpret_cast<u32*>(smem_dyn);
     uint2* s_tw = reinterpret_cast<uint2*>(ktile + CFG::TILE_WORDS);
-    uint2* s_itw_smem = s_tw + N;                                        // only when !HALF
-    u32* groups = reinterpret_cast<u32*>(s_tw + (HALF ? 1 : 2) * N);
+    uint2* s_itw_smem = s_tw + N;
+    u32* groups = reinterpret_cast<u32*>(s_tw + 2 * N);
     unsigned short* ca_all = reinterpret_cast<unsigned short*>(groups + (size_t)SLOTS * L1_GROUP_WORDS);
     u64* mbar = reinterpret_cast<u64*>(ca_all + SLOTS * CLUE_N);
 
@@ -161,7 +159,7 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
     unsigned short* ca = ca_all + slot * CLUE_N;
     ExBuf<u32> eb{acc + 2 * N, acc + 2 * N + GEO::BUF};
     if (threadIdx.x == 0) mbar_init(mbar, 1);
-    for (int i = threadIdx.x; i < N; i += THREADS) { s_tw[i] = tb.tw1[i]; if (!HALF) s_itw_smem[i] = tb.itw1[i]; }
+    for (int i = threadIdx.x; i < N; i += THREADS) { s_tw[i] = tb.tw1[i]; s_itw_smem[i] = tb.itw1[i]; }
     for (int i = t; i < CLUE_N; i += L1_GROUP) ca[i] = clue_a[(size_t)msg * CLUE_N + i] & (CLUE_Q - 1);   // canonical mod 2048
     init_acc<F, GEO>(acc, tb.lut1, clue_b[(size_t)msg * CLUE_COUNT + c] & (CLUE_Q - 1), t);
     __syncthreads();
@@ -180,18 +178,14 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
         for (int p = 0; p < 2; ++p) {
             i32 u[E];
             decompose_words<F, G, GEO>(u, acc + p * N, a, t);
-            if (HALF && p == 1) {
-                __syncthreads();                                                 // every group is done with the first half
-                if (threadIdx.x == 0) tma_load(ktile, bsk1 + (size_t)i * L1_TILE_WORDS + CFG::TILE_WORDS, CFG::TILE_WORDS * 4, mbar);
-            }
 #pragma unroll 1
             for (int r = 0; r < L; ++r) {
                 u32 x[E];
 #pragma unroll
                 for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, G>(u[k], r);
                 ntt_forward<AR, GEO, LdSharedC>(x, eb, s_tw, t, bar);
-                if (r == 0 && (p == 0 || HALF)) { mbar_wait(mbar, phase & 1); ++phase; }   // the (half) tile has landed
-                const u32* ka = ktile + (size_t)((HALF ? 0 : p * L) + r) * 2 * N + out_idx<GEO>(t, 0);
+                if (r == 0 && p == 0) { mbar_wait(mbar, phase & 1); ++phase; }             // tile i has landed
+                const u32* ka = ktile + (size_t)(p * L + r) * 2 * N + out_idx<GEO>(t, 0);
                 const u32* kb = ka + N;
 #pragma unroll
                 for (int k = 0; k < E; k += 4) {
@@ -208,8 +202,7 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
         __syncthreads();                                                         // every group is done with tile i
         if (threadIdx.x == 0 && i + 1 < CLUE_N) tma_load(ktile, bsk1 + (size_t)(i + 1) * L1_TILE_WORDS, CFG::TILE_WORDS * 4, mbar);
         // both inverse transforms in flight (two buffers, staggered exchanges): twice the ILP of running them back to back
-        if (HALF) ntt_inverse2s<AR, GEO, LdGlobal>(ya, yb, eb.a, eb.b, tb.itw1, t, bar);
-        else ntt_inverse2s<AR, GEO, LdShared>(ya, yb, eb.a, eb.b, s_itw_smem, t, bar);
+        ntt_inverse2s<AR, GEO, LdShared>(ya, yb, eb.a, eb.b, s_itw_smem, t, bar);
 #pragma unroll
         for (int k = 0; k < E; ++k) {
             const int pos = t + GEO::NT * k;
