@@ -226,24 +226,6 @@ __device__ __forceinline__ void ntt_forward(typename AR::T (&x)[GEO::E], ExBuf<t
         fwd_pass<AR, GEO, 3, LD>(x, tw, t);
     }
 }
-// two forward NTTs sharing the barriers (second polynomial uses its own buffer pair)
-template <class AR, class GEO, class LD>
-__device__ __forceinline__ void ntt_forward2(typename AR::T (&x)[GEO::E], typename AR::T (&y)[GEO::E], ExBuf<typename AR::T>& ex, ExBuf<typename AR::T>& ey,
-                                             const typename AR::TW* __restrict__ tw, int t, int bar) {
-    typedef typename AR::T T;
-    fwd_pass<AR, GEO, 0, LD>(x, tw, t); fwd_pass<AR, GEO, 0, LD>(y, tw, t);
-    { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 0, 0>(x, w, t); ex_store<GEO, 0, 0>(y, v, t); group_sync<GEO::NT>(bar);
-      ex_load<GEO, 1, 0>(x, w, t); ex_load<GEO, 1, 0>(y, v, t); }
-    fwd_pass<AR, GEO, 1, LD>(x, tw, t); fwd_pass<AR, GEO, 1, LD>(y, tw, t);
-    { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 1, 1>(x, w, t); ex_store<GEO, 1, 1>(y, v, t); group_sync<GEO::NT>(bar);
-      ex_load<GEO, 2, 1>(x, w, t); ex_load<GEO, 2, 1>(y, v, t); }
-    fwd_pass<AR, GEO, 2, LD>(x, tw, t); fwd_pass<AR, GEO, 2, LD>(y, tw, t);
-    if constexpr (GEO::NPASS == 4) {
-        { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 2, 2>(x, w, t); ex_store<GEO, 2, 2>(y, v, t); group_sync<GEO::NT>(bar);
-          ex_load<GEO, 3, 2>(x, w, t); ex_load<GEO, 3, 2>(y, v, t); }
-        fwd_pass<AR, GEO, 3, LD>(x, tw, t); fwd_pass<AR, GEO, 3, LD>(y, tw, t);
-    }
-}
 // Inverse NTT (unscaled): x holds last-pass elements on entry, pass-0 elements on exit.
 template <class AR, class GEO, class LD>
 __device__ __forceinline__ void ntt_inverse(typename AR::T (&x)[GEO::E], ExBuf<typename AR::T>& eb, const typename AR::TW* __restrict__ itw, int t, int bar) {
@@ -257,23 +239,6 @@ __device__ __forceinline__ void ntt_inverse(typename AR::T (&x)[GEO::E], ExBuf<t
     inv_pass<AR, GEO, 1, LD>(x, itw, t);
     { T* w = eb.next(); ex_store<GEO, 1, 0>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 0, 0>(x, w, t); }
     inv_pass<AR, GEO, 0, LD>(x, itw, t);
-}
-template <class AR, class GEO, class LD>
-__device__ __forceinline__ void ntt_inverse2(typename AR::T (&x)[GEO::E], typename AR::T (&y)[GEO::E], ExBuf<typename AR::T>& ex, ExBuf<typename AR::T>& ey,
-                                             const typename AR::TW* __restrict__ itw, int t, int bar) {
-    typedef typename AR::T T;
-    if constexpr (GEO::NPASS == 4) {
-        inv_pass<AR, GEO, 3, LD>(x, itw, t); inv_pass<AR, GEO, 3, LD>(y, itw, t);
-        { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 3, 2>(x, w, t); ex_store<GEO, 3, 2>(y, v, t); group_sync<GEO::NT>(bar);
-          ex_load<GEO, 2, 2>(x, w, t); ex_load<GEO, 2, 2>(y, v, t); }
-    }
-    inv_pass<AR, GEO, 2, LD>(x, itw, t); inv_pass<AR, GEO, 2, LD>(y, itw, t);
-    { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 2, 1>(x, w, t); ex_store<GEO, 2, 1>(y, v, t); group_sync<GEO::NT>(bar);
-      ex_load<GEO, 1, 1>(x, w, t); ex_load<GEO, 1, 1>(y, v, t); }
-    inv_pass<AR, GEO, 1, LD>(x, itw, t); inv_pass<AR, GEO, 1, LD>(y, itw, t);
-    { T* w = ex.next(); T* v = ey.next(); ex_store<GEO, 1, 0>(x, w, t); ex_store<GEO, 1, 0>(y, v, t); group_sync<GEO::NT>(bar);
-      ex_load<GEO, 0, 0>(x, w, t); ex_load<GEO, 0, 0>(y, v, t); }
-    inv_pass<AR, GEO, 0, LD>(x, itw, t); inv_pass<AR, GEO, 0, LD>(y, itw, t);
 }
 
 // Two transforms through only TWO buffers (x always via `bx`, y always via `by`), staggered so that every store to a
