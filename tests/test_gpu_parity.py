@@ -161,6 +161,22 @@ def test_weights_from_seed_match_reference_stream(detector):
         detector.weights_from_seed(b"short", 1, 1)
 
 
+def test_tensor_core_key_switch_is_exact(detector, keypack):
+    """From 1 024 messages the key switch runs as an int8 tensor-core GEMM (digits x key limbs, int32 accumulation, limbs
+    recombined mod q1).  Its words must equal the CUDA-core kernels' (split rows for <= 256 messages, one CTA per 16
+    messages above) on full-range random ciphertexts, and the oracle's on a sample — including saturated rows."""
+    import torch
+    rng = np.random.default_rng(21)
+    rl = rng.integers(0, O.Q1, (1030, 2, O.N1), dtype=np.uint32)
+    rl[5] = O.Q1 - 1; rl[6] = 0; rl[7, 0] = (O.Q1 - 1) // 2; rl[8, 0] = (O.Q1 + 1) // 2      # extreme digits: all -1 / 0 / +-max
+    d = _dev(rl, np.int32)
+    big = detector.key_switch(d); torch.cuda.synchronize()
+    parts = torch.cat([detector.key_switch(d[:256]), detector.key_switch(d[256:1000])]); torch.cuda.synchronize()
+    assert torch.equal(big[:1000], parts)
+    sample = np.array([0, 5, 6, 7, 8, 511, 1023, 1029])
+    assert np.array_equal(big.cpu().numpy().view(np.uint32)[sample], keypack.keyswitch(rl[sample]))
+
+
 def test_omd_acceptance(detector, keypack, decoy):
     """omr_core/examples/omd.rs:45-58: pertinent -> [1,0,...,0], non-pertinent -> all 0."""
     a, b = _mixed_clues(keypack, decoy, 2, [0], seed=21)

@@ -63,6 +63,9 @@ struct omr_ctx {
     size_t cap = 0; u32* s_rlwe1 = nullptr; u32* s_lwe2 = nullptr; unsigned short *s_ca = nullptr, *s_cb = nullptr;
     size_t cap7 = 0; u32* s_rlwe7 = nullptr;      // per-(message, clue) accumulators of the L1 kernel
     int l2c_max_clusters = 0;                     // co-resident 6-CTA clusters (cudaOccupancyMaxActiveClusters)
+    // tensor-core key switch (large batches): key limbs [KSG_N][KSG_K] int8, per-chunk digits / products / CUTLASS workspace
+    signed char* ksg_bt = nullptr; signed char* ksg_a = nullptr; i32* ksg_c = nullptr; void* ksg_ws = nullptr; size_t ksg_ws_bytes = 0;
+    bool ks_gemm = false;
     int* d_flag = nullptr;                        // "a weight draw was rejected" flag of omr_weights_from_seed_device
     double* l2c_scratch = nullptr;                // partial sums exchanged inside a level-2 cluster
     unsigned long long* ks_part = nullptr;        // [KS_SPLIT_MAXB][KSK_PAD] partial sums of the split key switch
@@ -78,6 +81,12 @@ struct omr_ctx {
     bool latency_shapes = true;                   // omr_set_latency_shapes / OMR_LATENCY_SHAPES=0: throughput shapes for every batch size
     // two-stream software pipeline of detect_device
 };
+
+namespace omr {            // ks_gemm.cu: the key switch as a tcgen05 int8 GEMM (CUTLASS collective), if it was compiled in
+int ks_gemm_i8(const int8_t* A, const int8_t* B, int32_t* C, int M, int N, int K, void* workspace, size_t workspace_bytes, cudaStream_t s);
+size_t ks_gemm_workspace(int M, int N, int K);
+bool ks_gemm_available();
+}
 
 namespace {
 void ctx_fail(omr_ctx* ctx, const std::string& m) { if (ctx) ctx->err = m; else g_create_error = m; }
@@ -127,6 +136,7 @@ int launch_l1(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, 
     return launch_l1_raw(ctx, ca, cb, B, ctx->s_rlwe7, out, s);
 }
 constexpr size_t KS_SPLIT_MAXB = 256;
+constexpr size_t KSG_MIN_B = 1024, KSG_CHUNK = 8192;      // tensor-core key switch: from 1 024 messages, 8 192 per GEMM
 int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s) {
     if (!B) return OMR_OK;
     dim3 grid((unsigned)((B + KS_MB - 1) / KS_MB), (KSK_PAD + KS_THREADS - 1) / KS_THREADS);
@@ -140,6 +150,25 @@ int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s)
         keyswitch_kernel<true><<<grid, KS_THREADS, KS_SMEM, s>>>(rlwe, ctx->ksk, out, (int)B, ctx->ks_part);
         keyswitch_finish_kernel<<<(unsigned)((B * KSK_PAD + 255) / 256), 256, 0, s>>>(rlwe, ctx->ks_part, out, (int)B);
         ctx->launches += 2; CK(cudaGetLastError());
+        return OMR_OK;
+    }
+    if (ctx->ks_gemm && B >= KSG_MIN_B) {
+        // large batch: digits x key limbs on the tensor cores, exact in int32; chunks bound the digit matrix (27 648 B per message)
+        if (!ctx->ksg_a) {
+            CK(cudaMalloc((void**)&ctx->ksg_a, KSG_CHUNK * (size_t)KSG_K));
+            CK(cudaMalloc((void**)&ctx->ksg_c, KSG_CHUNK * (size_t)KSG_N * sizeof(i32)));
+            ctx->ksg_ws_bytes = ks_gemm_workspace((int)KSG_CHUNK, KSG_N, KSG_K);
+            if (ctx->ksg_ws_bytes) CK(cudaMalloc(&ctx->ksg_ws, ctx->ksg_ws_bytes));
+        }
+        for (size_t off = 0; off < B; off += KSG_CHUNK) {
+            const size_t nb = B - off < KSG_CHUNK ? B - off : KSG_CHUNK;
+            const u32* r = rlwe + off * 2 * F1::N;
+            ks_digits_kernel<<<(unsigned)((nb * F1::N + 255) / 256), 256, 0, s>>>(r, ctx->ksg_a, (int)nb);
+            const int rc = ks_gemm_i8((const int8_t*)ctx->ksg_a, (const int8_t*)ctx->ksg_bt, ctx->ksg_c, (int)nb, KSG_N, KSG_K, ctx->ksg_ws, ctx->ksg_ws_bytes, s);
+            if (rc) { ctx_fail(ctx, "key switch GEMM failed (status " + std::to_string(rc) + ")"); return OMR_ERR_CUDA; }
+            ks_combine_kernel<<<(unsigned)((nb * (LWE2_N + 1) + 255) / 256), 256, 0, s>>>(r, ctx->ksg_c, out + off * LWE2_STRIDE_IN, (int)nb);
+            ctx->launches += 3; CK(cudaGetLastError());
+        }
         return OMR_OK;
     }
     keyswitch_kernel<false><<<grid, KS_THREADS, KS_SMEM, s>>>(rlwe, ctx->ksk, out, (int)B, nullptr);
@@ -376,6 +405,14 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         ksk_pad_kernel<<<(unsigned)((n_ksk_rows * KSK_PAD + 255) / 256), 256, 0, s>>>(tmp, ctx->ksk, n_ksk_rows); ++ctx->launches;
         CKC(cudaStreamSynchronize(s)); cudaFree(tmp);
     }
+    ctx->ks_gemm = ks_gemm_available();
+    if (const char* e = getenv("OMR_KS_GEMM")) ctx->ks_gemm = ctx->ks_gemm && atoi(e) != 0;
+    if (ctx->ks_gemm) {   // key limbs for the tensor-core key switch: [KSG_N][KSG_K] int8, 74 MB
+        CKC(cudaMalloc((void**)&ctx->ksg_bt, (size_t)KSG_N * KSG_K));
+        CKC(cudaMemsetAsync(ctx->ksg_bt, 0, (size_t)KSG_N * KSG_K, s));
+        ks_limbs_kernel<<<(unsigned)(((size_t)KSG_K * (KSG_N / KSG_LIMBS) + 255) / 256), 256, 0, s>>>(ctx->ksk, ctx->ksg_bt); ++ctx->launches;
+        CKC(cudaStreamSynchronize(s));
+    }
     const bool coeff = keys->flags == OMR_KEYS_COEFF;
     {
         const u32 c1 = h_mulmod<u32>((u32)(((u64)1 << 32) % Q1), n1i, Q1);
@@ -408,7 +445,7 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
-                    ctx->ks_part, ctx->l2c_scratch, ctx->d_flag, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
+                    ctx->ks_part, ctx->l2c_scratch, ctx->d_flag, ctx->ksg_bt, ctx->ksg_a, ctx->ksg_c, ctx->ksg_ws, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

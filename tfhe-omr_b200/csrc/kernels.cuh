@@ -653,6 +653,45 @@ __global__ void keyswitch_finish_kernel(const u32* __restrict__ rlwe, const unsi
     out[(size_t)m * LWE2_STRIDE_IN + col] = ks_finish((i64)part[e], rlwe[(size_t)m * 2 * F1::N + F1::N], col);
 }
 
+// K2 as a tensor-core GEMM (ks_gemm.cu): operand expansion and the epilogue.  K index = i * 27 + j, N index = col * 4 + limb.
+constexpr int KSG_K = F1::N * KS_LEVELS;                     // 27 648
+constexpr int KSG_LIMBS = 4, KSG_N = ((LWE2_N + 1) * KSG_LIMBS + 15) / 16 * 16;   // 2 688
+// A[m][i*27 + j] = balanced base-2 digit j of the extracted mask coefficient a'_i (the same digits keyswitch_kernel uses)
+__global__ void ks_digits_kernel(const u32* __restrict__ rlwe, signed char* __restrict__ A, int B) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)B * F1::N) return;
+    const int m = (int)(e / F1::N), i = (int)(e % F1::N);
+    const u32* a = rlwe + (size_t)m * 2 * F1::N;
+    const u32 ai = i == 0 ? a[0] : (a[F1::N - i] ? Q1 - a[F1::N - i] : 0);
+    const i32 v = ai > (Q1 >> 1) ? (i32)ai - (i32)Q1 : (i32)ai;
+    const i32 w = v + ((1 << 26) - 1);
+    signed char* o = A + (size_t)m * KSG_K + (size_t)i * KS_LEVELS;
+#pragma unroll
+    for (int j = 0; j < KS_LEVELS; ++j) o[j] = (signed char)(j < KS_LEVELS - 1 ? ((w >> j) & 1) - 1 : (w >> (KS_LEVELS - 1)));
+}
+// Bt[n = col*4 + limb][k = i*27 + j] = balanced base-256 limb of KSK[i][j][col] (device key layout: rows padded to KSK_PAD)
+__global__ void ks_limbs_kernel(const u32* __restrict__ ksk, signed char* __restrict__ Bt) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)KSG_K * (KSG_N / KSG_LIMBS)) return;
+    const int k = (int)(e % KSG_K), col = (int)(e / KSG_K);
+    u32 w = col <= LWE2_N ? ksk[(size_t)k * KSK_PAD + col] : 0u;
+#pragma unroll
+    for (int l = 0; l < KSG_LIMBS; ++l) {
+        i32 t = (i32)(w & 255u); w >>= 8;
+        if (t >= 128) { t -= 256; w += 1; }
+        Bt[((size_t)col * KSG_LIMBS + l) * KSG_K + k] = (signed char)t;
+    }
+}
+// sum = SUM_l C[m][col*4 + l] * 256^l, then the same final step as keyswitch_kernel
+__global__ void ks_combine_kernel(const u32* __restrict__ rlwe, const i32* __restrict__ C, u32* __restrict__ out, int B) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)B * (LWE2_N + 1)) return;
+    const int m = (int)(e / (LWE2_N + 1)), col = (int)(e % (LWE2_N + 1));
+    const int4 c = *reinterpret_cast<const int4*>(C + (size_t)m * KSG_N + (size_t)col * KSG_LIMBS);
+    const i64 sum = (i64)c.x + (i64)c.y * 256 + (i64)c.z * 65536 + (i64)c.w * 16777216;
+    out[(size_t)m * LWE2_STRIDE_IN + col] = ks_finish(sum, rlwe[(size_t)m * 2 * F1::N + F1::N], col);
+}
+
 // ---- K4: scale by N^-1, homomorphic trace, forward NTT ----------------------------------------------------------------
 // The 11 x 25 digit transforms, the MAC against the trace key and the inverse transforms run on the FP64 pipe like K3
 // (two digits per pass, key words = centred doubles x N^-1); the two final forward transforms (to_ntt_rlwe) stay integer.
