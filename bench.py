@@ -264,7 +264,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 2), "unit": "messages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
         "gpu_launches": int(launches),
         "latency": {"detect_one_message_ms": round(latency_ms, 3), "detect_one_message_host_api_ms": round(latency_host_ms, 3), "reference_ms": 243.6431,
-                    "note": "latency shapes: 7 level-1 CTAs (8 groups per rotation), split key switch, one 6-CTA cluster for level 2; reference: README.md:89-90, 1 thread"},
+                    "note": "latency shapes: 7 level-1 CTAs (8 groups per rotation), tensor-core key switch, one 6-CTA cluster for level 2; reference: README.md:89-90, 1 thread"},
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "l2_blind_rotate_kernel", "achieved": round(hbm_achieved, 3), "peak": peaks.get("hbm_gbs"),
                      "unit": "GB/s", "frac": round(hbm_achieved / peaks.get("hbm_gbs"), 6), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

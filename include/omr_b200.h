@@ -196,6 +196,12 @@ int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_seco
  * the throughput shapes.  Both give bit-identical results; enable = 0 forces the throughput shapes for every batch size. */
 int omr_set_latency_shapes(omr_ctx* ctx, int enable);
 
+/* Key switch on the tensor cores.  The LWE key switch (detector.rs:560-563) is a {-1,0,1} x u32 matrix product; when the
+ * library was built with the CUTLASS headers it runs as an exact int8 GEMM (tcgen05, int32 accumulation, key split into
+ * 8-bit limbs) at every batch size, otherwise — or with enable = 0 — as CUDA-core kernels.  Identical results.  Enabling it
+ * on a library built without it returns OMR_ERR_STATE. */
+int omr_set_tensor_core_key_switch(omr_ctx* ctx, int enable);
+
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
 uint64_t omr_launch_count(const omr_ctx* ctx);
 

@@ -75,6 +75,7 @@ def test_launch_shapes_agree(detector, keypack):
     rl = rng.integers(0, O.Q1, (256, 2, O.N1), dtype=np.uint32)
     lw = rng.integers(0, 4096, (148, 671), dtype=np.uint32)
     got = {}
+    detector.set_tensor_core_key_switch(False)              # compare the CUDA-core key-switch shapes with each other
     for lat in (True, False):
         detector.set_latency_shapes(lat)
         l1 = [detector.first_level_blind_rotate(_dev(a[:n], np.int16), _dev(b[:n], np.int16)) for n in (21, 22, 43)]
@@ -83,6 +84,7 @@ def test_launch_shapes_agree(detector, keypack):
         torch.cuda.synchronize()
         got[lat] = [x.cpu().numpy() for x in l1 + ks + l2]
     detector.set_latency_shapes(True)
+    detector.set_tensor_core_key_switch(True)
     for x, y in zip(got[True], got[False]):
         assert np.array_equal(x, y)
     # key switch of one message against the oracle on a random (full-range) ciphertext
@@ -100,6 +102,7 @@ def test_small_batch_exchanges_repeatable(detector):
     lw = rng.integers(0, 4096, (44, 671), dtype=np.uint32)
     rl = rng.integers(0, O.Q1, (40, 2, O.N1), dtype=np.uint32)
     da, db, dlw, drl = _dev(a, np.int16), _dev(b, np.int16), _dev(lw, np.int32), _dev(rl, np.int32)
+    detector.set_tensor_core_key_switch(False)              # the CUDA-core key switch with its integer atomics is the one under test
     detector.set_latency_shapes(False)
     want = [detector.first_level_blind_rotate(da, db), detector.second_level_blind_rotate(dlw[:22]), detector.second_level_blind_rotate(dlw),
             detector.key_switch(drl)]
@@ -111,6 +114,7 @@ def test_small_batch_exchanges_repeatable(detector):
         torch.cuda.synchronize()
         for x, y in zip(got, want):
             assert torch.equal(x, y)
+    detector.set_tensor_core_key_switch(True)
 
 
 def test_extreme_inputs_bit_exact(detector, keypack, shape):
@@ -162,19 +166,26 @@ def test_weights_from_seed_match_reference_stream(detector):
 
 
 def test_tensor_core_key_switch_is_exact(detector, keypack):
-    """From 1 024 messages the key switch runs as an int8 tensor-core GEMM (digits x key limbs, int32 accumulation, limbs
-    recombined mod q1).  Its words must equal the CUDA-core kernels' (split rows for <= 256 messages, one CTA per 16
-    messages above) on full-range random ciphertexts, and the oracle's on a sample — including saturated rows."""
+    """The key switch runs as an int8 tensor-core GEMM (digits x key limbs, int32 accumulation, limbs recombined mod q1).
+    Its words must equal the CUDA-core kernels' (split rows for <= 256 messages, one CTA per 16 messages above) on
+    full-range random ciphertexts at ragged batch sizes, and the oracle's on a sample — including saturated rows."""
     import torch
     rng = np.random.default_rng(21)
     rl = rng.integers(0, O.Q1, (1030, 2, O.N1), dtype=np.uint32)
     rl[5] = O.Q1 - 1; rl[6] = 0; rl[7, 0] = (O.Q1 - 1) // 2; rl[8, 0] = (O.Q1 + 1) // 2      # extreme digits: all -1 / 0 / +-max
     d = _dev(rl, np.int32)
-    big = detector.key_switch(d); torch.cuda.synchronize()
-    parts = torch.cat([detector.key_switch(d[:256]), detector.key_switch(d[256:1000])]); torch.cuda.synchronize()
-    assert torch.equal(big[:1000], parts)
+    sizes = (1, 9, 256, 257, 1030)
+    detector.set_tensor_core_key_switch(True)
+    tc = [detector.key_switch(d[:n]) for n in sizes]; torch.cuda.synchronize()
+    try:
+        detector.set_tensor_core_key_switch(False)
+        cc = [detector.key_switch(d[:n]) for n in sizes]; torch.cuda.synchronize()
+    finally:
+        detector.set_tensor_core_key_switch(True)
+    for x, y in zip(tc, cc):
+        assert torch.equal(x, y)
     sample = np.array([0, 5, 6, 7, 8, 511, 1023, 1029])
-    assert np.array_equal(big.cpu().numpy().view(np.uint32)[sample], keypack.keyswitch(rl[sample]))
+    assert np.array_equal(tc[-1].cpu().numpy().view(np.uint32)[sample], keypack.keyswitch(rl[sample]))
 
 
 def test_omd_acceptance(detector, keypack, decoy):

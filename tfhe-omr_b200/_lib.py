@@ -15,7 +15,7 @@ EXPORTS = [
     "omr_retrieval_params_init", "omr_detect_batch", "omr_pv_reset", "omr_encode_indices", "omr_encode_payloads",
     "omr_detect_batch_device", "omr_encode_indices_device", "omr_encode_payloads_device", "omr_digest_reduce_mod",
     "omr_l1_blind_rotate_device", "omr_keyswitch_device", "omr_l2_blind_rotate_device", "omr_trace_device",
-    "omr_ntt_forward_device", "omr_ntt_inverse_device", "omr_launch_count", "omr_mulmod_peak", "omr_digest_add_mod", "omr_decrypt_decode_device", "omr_gen_clues_device", "omr_set_latency_shapes", "omr_decode_digest", "omr_weights_from_seed_device", "omr_encode_payloads_seeded",
+    "omr_ntt_forward_device", "omr_ntt_inverse_device", "omr_launch_count", "omr_mulmod_peak", "omr_digest_add_mod", "omr_decrypt_decode_device", "omr_gen_clues_device", "omr_set_latency_shapes", "omr_decode_digest", "omr_weights_from_seed_device", "omr_encode_payloads_seeded", "omr_set_tensor_core_key_switch",
 ]
 
 
@@ -55,6 +55,7 @@ def load():
     L.omr_detect_key_size.restype = sz; L.omr_detect_key_size.argtypes = [vp]
     L.omr_launch_count.restype = u64; L.omr_launch_count.argtypes = [vp]
     L.omr_set_latency_shapes.restype = i32; L.omr_set_latency_shapes.argtypes = [vp, i32]
+    L.omr_set_tensor_core_key_switch.restype = i32; L.omr_set_tensor_core_key_switch.argtypes = [vp, i32]
     L.omr_weights_from_seed_device.restype = i32; L.omr_weights_from_seed_device.argtypes = [vp, C.c_char_p, sz, vp, u32, vp]
     L.omr_encode_payloads_seeded.restype = i32; L.omr_encode_payloads_seeded.argtypes = [vp, vp, sz, C.c_char_p, u64, u32, u32, vp]
     L.omr_decode_digest.restype = i32

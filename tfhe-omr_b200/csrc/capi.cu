@@ -65,7 +65,7 @@ struct omr_ctx {
     int l2c_max_clusters = 0;                     // co-resident 6-CTA clusters (cudaOccupancyMaxActiveClusters)
     // tensor-core key switch (large batches): key limbs [KSG_N][KSG_K] int8, per-chunk digits / products / CUTLASS workspace
     signed char* ksg_bt = nullptr; signed char* ksg_a = nullptr; i32* ksg_c = nullptr; void* ksg_ws = nullptr; size_t ksg_ws_bytes = 0;
-    bool ks_gemm = false;
+    bool ks_gemm = false; size_t ksg_min_b = KSG_MIN_B;
     int* d_flag = nullptr;                        // "a weight draw was rejected" flag of omr_weights_from_seed_device
     double* l2c_scratch = nullptr;                // partial sums exchanged inside a level-2 cluster
     unsigned long long* ks_part = nullptr;        // [KS_SPLIT_MAXB][KSK_PAD] partial sums of the split key switch
@@ -136,11 +136,11 @@ int launch_l1(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, 
     return launch_l1_raw(ctx, ca, cb, B, ctx->s_rlwe7, out, s);
 }
 constexpr size_t KS_SPLIT_MAXB = 256;
-constexpr size_t KSG_MIN_B = 1024, KSG_CHUNK = 8192;      // tensor-core key switch: from 1 024 messages, 8 192 per GEMM
 int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s) {
     if (!B) return OMR_OK;
     dim3 grid((unsigned)((B + KS_MB - 1) / KS_MB), (KSK_PAD + KS_THREADS - 1) / KS_THREADS);
-    if (B <= KS_SPLIT_MAXB && ctx->latency_shapes) {
+    const bool gemm = ctx->ks_gemm && B >= ctx->ksg_min_b;
+    if (!gemm && B <= KS_SPLIT_MAXB && ctx->latency_shapes) {
         // small batch: too few CTAs to fill the GPU and each walks 27 648 key rows serially -> split the rows
         if (!ctx->ks_part) CK(cudaMalloc((void**)&ctx->ks_part, KS_SPLIT_MAXB * KSK_PAD * sizeof(unsigned long long)));
         unsigned z = 1;
@@ -152,7 +152,7 @@ int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s)
         ctx->launches += 2; CK(cudaGetLastError());
         return OMR_OK;
     }
-    if (ctx->ks_gemm && B >= KSG_MIN_B) {
+    if (gemm) {
         // large batch: digits x key limbs on the tensor cores, exact in int32; chunks bound the digit matrix (27 648 B per message)
         if (!ctx->ksg_a) {
             CK(cudaMalloc((void**)&ctx->ksg_a, KSG_CHUNK * (size_t)KSG_K));
@@ -407,6 +407,7 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     }
     ctx->ks_gemm = ks_gemm_available();
     if (const char* e = getenv("OMR_KS_GEMM")) ctx->ks_gemm = ctx->ks_gemm && atoi(e) != 0;
+    if (const char* e = getenv("OMR_KS_GEMM_MIN")) { long v = atol(e); if (v >= 1) ctx->ksg_min_b = (size_t)v; }
     if (ctx->ks_gemm) {   // key limbs for the tensor-core key switch: [KSG_N][KSG_K] int8, 74 MB
         CKC(cudaMalloc((void**)&ctx->ksg_bt, (size_t)KSG_N * KSG_K));
         CKC(cudaMemsetAsync(ctx->ksg_bt, 0, (size_t)KSG_N * KSG_K, s));
@@ -455,6 +456,12 @@ void omr_ctx_destroy(omr_ctx* ctx) {
 const char* omr_last_error(const omr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 size_t omr_detect_key_size(const omr_ctx* ctx) { return ctx ? ctx->key_bytes : 0; }
 uint64_t omr_launch_count(const omr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int omr_set_tensor_core_key_switch(omr_ctx* ctx, int enable) {
+    if (!ctx) return OMR_ERR_INVALID;
+    if (enable && !ctx->ksg_bt) { ctx_fail(ctx, "the tensor-core key switch was not built into this library or is disabled (OMR_KS_GEMM=0)"); return OMR_ERR_STATE; }
+    ctx->ks_gemm = enable != 0;
+    return OMR_OK;
+}
 int omr_set_latency_shapes(omr_ctx* ctx, int enable) {
     if (!ctx) return OMR_ERR_INVALID;
     ctx->latency_shapes = enable != 0;

@@ -144,6 +144,10 @@ class Detector:
         self._ck(self.L.omr_weights_from_seed_device(self.h, seed, rows * cols, out.data_ptr(), 1 if in_order else 0, self._stream()))
         return out
 
+    def set_tensor_core_key_switch(self, enable):
+        """omr_set_tensor_core_key_switch: the key switch as an int8 tensor-core GEMM (default when built in) or on CUDA cores."""
+        self._ck(self.L.omr_set_tensor_core_key_switch(self.h, 1 if enable else 0))
+
     def set_latency_shapes(self, enable):
         """omr_set_latency_shapes: small batches use the latency launch shapes (default) or the throughput shapes."""
         self._ck(self.L.omr_set_latency_shapes(self.h, 1 if enable else 0))
