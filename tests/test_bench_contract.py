@@ -24,7 +24,7 @@ def _common(d):
 
 
 def test_our_line():
-    for name, n in (("r1_bench_g.json", 1), ("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4), ("r1_bench_n8.json", 8)):
+    for name, n in (("r1_bench_h.json", 1), ("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4), ("r1_bench_n8.json", 8)):
         d = _line(name)
         assert d["n_gpus"] == n and d["warmup"] >= 3 and d["gpu_launches"] > 0 and "impl" not in d
         if n == 1:
@@ -38,7 +38,7 @@ def test_our_line():
         clk = d["clocks"]
         assert clk["sm_mhz"] > 0 and clk["sm_max_mhz"] >= clk["sm_mhz"] and isinstance(clk["reasons"], list)
         assert not set(clk["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    v = [_line(f"r1_bench_{s}.json")["value"] for s in ("g", "n2", "n4", "n8")]
+    v = [_line(f"r1_bench_{s}.json")["value"] for s in ("h", "n2", "n4", "n8")]
     assert v[0] < v[1] < v[2] < v[3]                       # whole-job aggregate grows with the number of GPUs
 
 
@@ -47,4 +47,4 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["gpu_launches"] == 0
     _common(d)
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
-    assert d["metric"] == _line("r1_bench_g.json")["metric"] and d["unit"] == _line("r1_bench_g.json")["unit"]
+    assert d["metric"] == _line("r1_bench_h.json")["metric"] and d["unit"] == _line("r1_bench_h.json")["unit"]
