@@ -163,7 +163,7 @@ int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s)
         for (size_t off = 0; off < B; off += KSG_CHUNK) {
             const size_t nb = B - off < KSG_CHUNK ? B - off : KSG_CHUNK;
             const u32* r = rlwe + off * 2 * F1::N;
-            ks_digits_kernel<<<(unsigned)((nb * F1::N + 255) / 256), 256, 0, s>>>(r, ctx->ksg_a, (int)nb);
+            ks_digits_kernel<<<(unsigned)((nb * (KSG_K / 16) + 255) / 256), 256, 0, s>>>(r, ctx->ksg_a, (int)nb);
             const int rc = ks_gemm_i8((const int8_t*)ctx->ksg_a, (const int8_t*)ctx->ksg_bt, ctx->ksg_c, (int)nb, KSG_N, KSG_K, ctx->ksg_ws, ctx->ksg_ws_bytes, s);
             if (rc) { ctx_fail(ctx, "key switch GEMM failed (status " + std::to_string(rc) + ")"); return OMR_ERR_CUDA; }
             ks_combine_kernel<<<(unsigned)((nb * (LWE2_N + 1) + 255) / 256), 256, 0, s>>>(r, ctx->ksg_c, out + off * LWE2_STRIDE_IN, (int)nb);

@@ -657,18 +657,29 @@ __global__ void keyswitch_finish_kernel(const u32* __restrict__ rlwe, const unsi
 constexpr int KSG_K = F1::N * KS_LEVELS;                     // 27 648
 constexpr size_t KSG_MIN_B = 1, KSG_CHUNK = 8192;            // faster than the CUDA-core kernels at every batch size; 8 192 messages per GEMM
 constexpr int KSG_LIMBS = 4, KSG_N = ((LWE2_N + 1) * KSG_LIMBS + 15) / 16 * 16;   // 2 688
-// A[m][i*27 + j] = balanced base-2 digit j of the extracted mask coefficient a'_i (the same digits keyswitch_kernel uses)
-__global__ void ks_digits_kernel(const u32* __restrict__ rlwe, signed char* __restrict__ A, int B) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (size_t)B * F1::N) return;
-    const int m = (int)(e / F1::N), i = (int)(e % F1::N);
-    const u32* a = rlwe + (size_t)m * 2 * F1::N;
-    const u32 ai = i == 0 ? a[0] : (a[F1::N - i] ? Q1 - a[F1::N - i] : 0);
+// A[m][i*27 + j] = balanced base-2 digit j of the extracted mask coefficient a'_i (the same digits keyswitch_kernel uses).
+// One thread writes 16 consecutive bytes of a row (coalesced 16-byte stores); they span at most two coefficients.
+__device__ __forceinline__ i32 ks_offset_word(const u32* __restrict__ a, int i) {
+    const u32 ai = i == 0 ? a[0] : (a[F1::N - i] ? Q1 - a[F1::N - i] : 0);      // a' = (a0, -a_{N-1}, ..., -a_1)
     const i32 v = ai > (Q1 >> 1) ? (i32)ai - (i32)Q1 : (i32)ai;
-    const i32 w = v + ((1 << 26) - 1);
-    signed char* o = A + (size_t)m * KSG_K + (size_t)i * KS_LEVELS;
+    return v + ((1 << 26) - 1);                                                  // offset word, base 2, 27 levels
+}
+__global__ void ks_digits_kernel(const u32* __restrict__ rlwe, signed char* __restrict__ A, int B) {
+    constexpr int CH = KSG_K / 16;                                               // 1 728 chunks of 16 bytes per message
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)B * CH) return;
+    const int m = (int)(e / CH), k0 = (int)(e % CH) * 16;
+    const u32* a = rlwe + (size_t)m * 2 * F1::N;
+    int i = k0 / KS_LEVELS, j = k0 % KS_LEVELS;
+    i32 w = ks_offset_word(a, i);
+    u32 pack[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < KS_LEVELS; ++j) o[j] = (signed char)(j < KS_LEVELS - 1 ? ((w >> j) & 1) - 1 : (w >> (KS_LEVELS - 1)));
+    for (int b = 0; b < 16; ++b) {
+        const i32 d = j < KS_LEVELS - 1 ? ((w >> j) & 1) - 1 : (w >> (KS_LEVELS - 1));
+        pack[b >> 2] |= (u32)(d & 0xFF) << (8 * (b & 3));
+        if (++j == KS_LEVELS) { j = 0; ++i; if (i < F1::N) w = ks_offset_word(a, i); }
+    }
+    *reinterpret_cast<uint4*>(A + (size_t)m * KSG_K + k0) = make_uint4(pack[0], pack[1], pack[2], pack[3]);
 }
 // Bt[n = col*4 + limb][k = i*27 + j] = balanced base-256 limb of KSK[i][j][col] (device key layout: rows padded to KSK_PAD)
 __global__ void ks_limbs_kernel(const u32* __restrict__ ksk, signed char* __restrict__ Bt) {
