@@ -655,7 +655,7 @@ __global__ void keyswitch_finish_kernel(const u32* __restrict__ rlwe, const unsi
 
 // K2 as a tensor-core GEMM (ks_gemm.cu): operand expansion and the epilogue.  K index = i * 27 + j, N index = col * 4 + limb.
 constexpr int KSG_K = F1::N * KS_LEVELS;                     // 27 648
-constexpr size_t KSG_MIN_B = 1, KSG_CHUNK = 8192;            // faster than the CUDA-core kernels at every batch size; 8 192 messages per GEMM
+constexpr size_t KSG_MIN_B = 1, KSG_CHUNK = 2048;            // faster than the CUDA-core kernels at every batch size; 2 048 messages per GEMM (79 MB of scratch)
 constexpr int KSG_LIMBS = 4, KSG_N = ((LWE2_N + 1) * KSG_LIMBS + 15) / 16 * 16;   // 2 688
 // A[m][i*27 + j] = balanced base-2 digit j of the extracted mask coefficient a'_i (the same digits keyswitch_kernel uses).
 // One thread writes 16 consecutive bytes of a row (coalesced 16-byte stores); they span at most two coefficients.
