@@ -159,6 +159,10 @@ def test_weights_from_seed_match_reference_stream(detector):
         got = detector.weights_from_seed(seed, rows, cols); torch.cuda.synchronize()
         assert np.array_equal(got.cpu().numpy().view(np.uint16), ref)
         assert ref.max() < 257
+    # without the oracle: the all-zero seed's first draws follow from the published ChaCha12 zero-key block
+    words = np.frombuffer(bytes.fromhex("9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"), dtype="<u4").astype(np.uint64)
+    got0 = detector.weights_from_seed(bytes(32), 1, 8); torch.cuda.synchronize()
+    assert np.array_equal(got0.cpu().numpy().view(np.uint16)[0], ((words * 257) >> 32).astype(np.uint16))
     ordered = detector.weights_from_seed(bytes([7] * 32), 3, 1000, in_order=True); torch.cuda.synchronize()
     assert np.array_equal(ordered.cpu().numpy().view(np.uint16), O.chacha12_weights(bytes([7] * 32), 3000).reshape(3, 1000))
     with pytest.raises(Exception):

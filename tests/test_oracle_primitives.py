@@ -86,12 +86,24 @@ def test_reduce128_special_form():
         assert O.lib().orc_reduce128_q2(hi, lo) == ((hi << 64) | lo) % O.Q2 == O.lib().orc_mod128_q2(hi, lo)
 
 
+CHACHA12_ZERO_KEY_BLOCK0_HEAD = "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+
+
 def test_chacha_core_against_chacha20_vector():
     """ChaCha20 block 0, zero key / nonce (the original ChaCha test vector, also RFC 7539 §2.3 structure);
     the weight stream uses the same core with 12 rounds (rand 0.8 StdRng)."""
     key = np.zeros(8, np.uint32); out = np.zeros(16, np.uint32)
     O.lib().orc_chacha_block(O.ptr(key), 0, 0, 20, O.ptr(out))
     assert out.tobytes()[:16].hex() == "76b8e0ada0f13d90405d6ae55386bd28"
+    # the 12-round core the weight stream actually uses (rand 0.8 StdRng = ChaCha12): published zero-key / zero-nonce
+    # test vector of ChaCha12 (and of ChaCha8 for good measure)
+    O.lib().orc_chacha_block(O.ptr(key), 0, 0, 12, O.ptr(out))
+    assert out.tobytes()[:32].hex() == CHACHA12_ZERO_KEY_BLOCK0_HEAD
+    O.lib().orc_chacha_block(O.ptr(key), 0, 0, 8, O.ptr(out))
+    assert out.tobytes()[:32].hex() == "3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e"
+    # the first draws for the all-zero seed follow from that block: Uniform(0, 257) takes the high word of u32 * 257
+    words = np.frombuffer(bytes.fromhex(CHACHA12_ZERO_KEY_BLOCK0_HEAD), dtype="<u4").astype(np.uint64)
+    assert np.array_equal(O.chacha12_weights(bytes(32), 8), ((words * 257) >> 32).astype(np.uint16))
     w = O.chacha12_weights(bytes(range(32)), 5000)
     assert w.max() <= 256 and w.min() == 0 and abs(float(w.mean()) - 128) < 4
     assert np.array_equal(w[:100], O.chacha12_weights(bytes(range(32)), 100))
