@@ -958,8 +958,8 @@ inline int decode_digest(const SecretKeyPack& sk, const RetrievalParams& rp, con
 // Weight stream of the reference: StdRng::from_seed(seed) (rand 0.8 => ChaCha12, 64-bit counter, stream 0)
 // + Uniform::<u16>::new(0,257).sample (widening-multiply rejection on one u32 per draw) — detector.rs:376-387,
 // retriever.rs:215-226 [UPSTREAM rand 0.8 / rand_chacha 0.3].  Restated from the published algorithms; parity
-// with the Rust crates is unpinned (no Rust here); the ChaCha core is checked against the RFC 7539 ChaCha20
-// zero-key block in tests.
+// with the Rust crates is unpinned (no Rust here); the ChaCha core is checked against the published zero-key
+// blocks of ChaCha20 (RFC 7539), ChaCha12 and ChaCha8 in tests.
 // ---------------------------------------------------------------------------
 inline void chacha_block(const u32 key[8], u64 counter, u64 stream, int rounds, u32 out[16]) {
     u32 st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5],
