@@ -73,14 +73,14 @@ def test_launch_shapes_agree(detector, keypack):
     rng = np.random.default_rng(5)
     a = rng.integers(0, 2048, (43, 512), dtype=np.uint16); b = rng.integers(0, 2048, (43, 7), dtype=np.uint16)
     rl = rng.integers(0, O.Q1, (256, 2, O.N1), dtype=np.uint32)
-    lw = rng.integers(0, 4096, (148, 671), dtype=np.uint32)
+    lw = rng.integers(0, 4096, (300, 671), dtype=np.uint32)
     got = {}
     detector.set_tensor_core_key_switch(False)              # compare the CUDA-core key-switch shapes with each other
     for lat in (True, False):
         detector.set_latency_shapes(lat)
         l1 = [detector.first_level_blind_rotate(_dev(a[:n], np.int16), _dev(b[:n], np.int16)) for n in (21, 22, 43)]
         ks = [detector.key_switch(_dev(rl[:n], np.int32)) for n in (1, 17, 256)]
-        l2 = [detector.second_level_blind_rotate(_dev(lw[:n], np.int32)) for n in (1, 24, 47, 148)]
+        l2 = [detector.second_level_blind_rotate(_dev(lw[:n], np.int32)) for n in (1, 24, 47, 148, 280, 300)]
         torch.cuda.synchronize()
         got[lat] = [x.cpu().numpy() for x in l1 + ks + l2]
     detector.set_latency_shapes(True)

@@ -175,6 +175,15 @@ int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s)
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
+// The 512-thread shape (one message per SM, a wave of n_sm messages in ~13.8 ms) has 97 % of the per-message throughput of the
+// 256-thread shape (two messages per SM, a wave of 2 n_sm messages in ~26.8 ms) at half the wave granularity: whichever has
+// the shorter sum of whole waves wins (the 512-thread one for every batch up to a few hundred messages, never for large ones).
+bool l2_prefers_wide_ctas(size_t B, size_t n_sm) {
+    if (B + 8 <= 2 * n_sm) return true;            // one or two waves of wide CTAs; a partial wave of the narrow shape measures 30-32 ms
+    if (B > 8 * n_sm) return false;
+    const size_t waves_wide = (B + n_sm - 1) / n_sm, waves_narrow = (B + 2 * n_sm - 1) / (2 * n_sm);
+    return 138 * waves_wide < 268 * waves_narrow;
+}
 int launch_l2(omr_ctx* ctx, const u32* lwe, size_t B, u64* out, cudaStream_t s) {
     if (!B) return OMR_OK;
     // a cluster of 6 SMs per message: one wave of clusters takes ~1/3 of the time of the 512-thread shape, so up to two waves win
@@ -183,7 +192,7 @@ int launch_l2(omr_ctx* ctx, const u32* lwe, size_t B, u64* out, cudaStream_t s) 
         if (!ctx->l2c_scratch) CK(cudaMalloc((void**)&ctx->l2c_scratch, cap * L2C_SCRATCH_WORDS * sizeof(double)));
         l2_blind_rotate_cluster_kernel<<<(unsigned)(B * L2C_CLUSTER), GeoL2::NT, L2C_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out,
                                                                                                  ctx->l2c_scratch, ctx->tb);
-    } else if (B <= (size_t)ctx->n_sm && ctx->latency_shapes)  // fewer messages than SMs: 512 threads per message
+    } else if (ctx->latency_shapes && l2_prefers_wide_ctas(B, (size_t)ctx->n_sm))
         l2_blind_rotate_lat_kernel<<<(unsigned)B, L2L_THREADS, L2L_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out, ctx->tb);
     else
         l2_blind_rotate_kernel<<<(unsigned)B, L2_THREADS, L2_SMEM, s>>>(lwe, reinterpret_cast<const double*>(ctx->bsk2), out, ctx->tb);
