@@ -67,18 +67,18 @@ def test_stages_bit_exact(detector, keypack, decoy, shape):
 
 def test_launch_shapes_agree(detector, keypack):
     """Latency and throughput shapes of every stage give identical words on random (not clue-shaped) inputs, including
-    batch sizes at the switch-over points (level 1: 21 / 22 / 43 messages = one rotation per CTA / two / four; level 2:
-    clusters up to ~24 messages, 512-thread CTAs up to 148; key switch: split rows up to 256 messages)."""
+    batch sizes around the switch-over points (level 1: one rotation per CTA in one or several waves / four / eight per CTA;
+    level 2: clusters up to ~44 messages, 512-thread CTAs, 256-thread CTAs; key switch: split rows up to 256 messages)."""
     import torch
     rng = np.random.default_rng(5)
-    a = rng.integers(0, 2048, (43, 512), dtype=np.uint16); b = rng.integers(0, 2048, (43, 7), dtype=np.uint16)
+    a = rng.integers(0, 2048, (200, 512), dtype=np.uint16); b = rng.integers(0, 2048, (200, 7), dtype=np.uint16)
     rl = rng.integers(0, O.Q1, (256, 2, O.N1), dtype=np.uint32)
     lw = rng.integers(0, 4096, (300, 671), dtype=np.uint32)
     got = {}
     detector.set_tensor_core_key_switch(False)              # compare the CUDA-core key-switch shapes with each other
     for lat in (True, False):
         detector.set_latency_shapes(lat)
-        l1 = [detector.first_level_blind_rotate(_dev(a[:n], np.int16), _dev(b[:n], np.int16)) for n in (21, 22, 43)]
+        l1 = [detector.first_level_blind_rotate(_dev(a[:n], np.int16), _dev(b[:n], np.int16)) for n in (21, 22, 43, 100, 200)]
         ks = [detector.key_switch(_dev(rl[:n], np.int32)) for n in (1, 17, 256)]
         l2 = [detector.second_level_blind_rotate(_dev(lw[:n], np.int32)) for n in (1, 24, 47, 148, 280, 300)]
         torch.cuda.synchronize()
@@ -88,7 +88,8 @@ def test_launch_shapes_agree(detector, keypack):
     for x, y in zip(got[True], got[False]):
         assert np.array_equal(x, y)
     # key switch of one message against the oracle on a random (full-range) ciphertext
-    assert np.array_equal(got[True][3].view(np.uint32).reshape(1, -1)[:, :671], keypack.keyswitch(rl[:1]))
+    first_ks = 5                                                # position of key_switch(rl[:1]) after the five level-1 outputs
+    assert np.array_equal(got[True][first_ks].view(np.uint32).reshape(1, -1)[:, :671], keypack.keyswitch(rl[:1]))
 
 
 def test_small_batch_exchanges_repeatable(detector):

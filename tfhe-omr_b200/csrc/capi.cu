@@ -209,12 +209,21 @@ int launch_trace(omr_ctx* ctx, u64* ct, size_t B, cudaStream_t s) {
 // L1 kernel into caller-provided per-clue buffer (no internal allocation); the shape follows the number of blind rotations
 int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* rlwe7, u32* out, cudaStream_t s) {
     const size_t n_clues = B * CLUE_COUNT;
-    // latency shape: with fewer blind rotations than SMs every rotation gets an SM of its own (8 groups share one rotation)
-    if (n_clues <= (size_t)ctx->n_sm && ctx->latency_shapes)
+    // Shape = rotations per CTA (1 = the 8-groups-per-rotation latency kernel).  One wave of n_sm CTAs takes about 2.6 / 7.4 /
+    // 13.2 ms for 1 / 4 / 8 rotations per CTA (2 per CTA, 5.4 ms, never beats two waves of the latency kernel); small and mid-size batches take the shape with the shortest sum of
+    // whole waves, large ones (where the tail wave is negligible) the 8-rotation shape with the best per-rotation cost.
+    int shape = 8;
+    if (ctx->latency_shapes && n_clues <= 16 * (size_t)ctx->n_sm) {
+        const int slots[3] = {1, 4, 8}, wave_us[3] = {2600, 7400, 13200};
+        size_t best = ~(size_t)0;
+        for (int k = 0; k < 3; ++k) {
+            const size_t ctas = (n_clues + slots[k] - 1) / slots[k], waves = (ctas + ctx->n_sm - 1) / ctx->n_sm, cost = waves * wave_us[k];
+            if (cost < best) { best = cost; shape = slots[k]; }
+        }
+    }
+    if (shape == 1)
         l1_blind_rotate_lat_kernel<<<(unsigned)n_clues, L1L_THREADS, L1L_SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, ctx->tb);
-    else if (n_clues <= 2 * (size_t)ctx->n_sm && ctx->latency_shapes)      // mid-size batches: fewer rotations per CTA, every SM busy
-        l1_blind_rotate_kernel<2><<<(unsigned)((n_clues + 1) / 2), L1Cfg<2>::THREADS, L1Cfg<2>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
-    else if (n_clues <= 4 * (size_t)ctx->n_sm && ctx->latency_shapes)
+    else if (shape == 4)
         l1_blind_rotate_kernel<4><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4>::THREADS, L1Cfg<4>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     else
         l1_blind_rotate_kernel<8><<<(unsigned)((n_clues + 7) / 8), L1Cfg<8>::THREADS, L1Cfg<8>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
@@ -371,7 +380,6 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     }
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<8>::SMEM));
     CKC(cudaFuncSetAttribute(l1_blind_rotate_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1L_SMEM));
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<2>::SMEM));
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<4>::SMEM));
     { cudaDeviceProp prop; CKC(cudaGetDeviceProperties(&prop, device)); ctx->n_sm = prop.multiProcessorCount; }
     // always carve out the maximum shared memory for the big kernels: with the driver's default heuristic an occasional

@@ -128,8 +128,8 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, u32 bytes, 
 constexpr int L1_GROUP = GeoL1::NT;                        // 64
 constexpr int L1_TILE_WORDS = 2 * G1::LEVELS * 2 * F1::N;  // 16384 u32 = 64 KiB
 constexpr int L1_GROUP_WORDS = 2 * F1::N + 2 * GeoL1::BUF;
-// SLOTS = blind rotations per CTA: 8 fills an SM (512 threads); 4 and 2 serve mid-size batches that could not give every
-// SM an 8-rotation CTA (capi.cu: launch_l1_raw).
+// SLOTS = blind rotations per CTA: 8 fills an SM (512 threads); 4 serves mid-size batches that could not give every SM an
+// 8-rotation CTA (capi.cu: launch_l1_raw).
 template <int SLOTS> struct L1Cfg {
     static constexpr int THREADS = SLOTS * L1_GROUP;
     static constexpr int TILE_WORDS = L1_TILE_WORDS;
