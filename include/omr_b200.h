@@ -14,9 +14,11 @@
  *   RLWE (a, b): b = a*s + m + e.   RGSW rows: [0,L) = RLWE(-s*m*g_j), [L,2L) = RLWE(m*g_j), g_j = 2^(drop + w*j).
  *
  * Concurrency.  The reference shares one `&Detector` between rayon workers (examples/omr.rs:160-164); here the batch IS the
- * parallelism.  The host-buffer calls (omr_detect_batch, omr_encode_*) take the context's mutex and may be called from any
- * thread.  The *_device calls use scratch buffers owned by the context: calls on one context must be ordered on ONE stream
- * (or externally serialised); use one context per stream — or per recipient key — for concurrent work on a GPU.
+ * parallelism.  The host-buffer calls (omr_detect_batch, omr_encode_*, omr_stream_*, omr_decode_digest) hold the context's
+ * mutex from the first launch until their result has been copied out, and may be called from any thread.  The *_device calls
+ * use scratch buffers owned by the context: calls on one context must be ordered on ONE stream (or externally serialised);
+ * use one context per stream — or per recipient key — for concurrent work on a GPU.  Every call runs on the context's device
+ * and restores the caller's current CUDA device before returning.
  */
 #ifndef OMR_B200_H
 #define OMR_B200_H
@@ -49,6 +51,14 @@ typedef enum {
 /* key-blob flags */
 #define OMR_KEYS_NTT_NATIVE 0u /* ring polynomials already in this library's NTT convention (above) */
 #define OMR_KEYS_COEFF 1u      /* ring polynomials in coefficient form; transformed on upload (Rust-shim path) */
+
+/* Domain of the ring polynomials that cross the HOST-buffer boundary after the keys (omr_set_output_domain): the pertinency
+ * ciphertexts of omr_detect_batch, the digests of omr_encode_indices / omr_encode_payloads*, the running digest of
+ * omr_stream_snapshot, and the ciphertexts / secret handed to omr_decode_digest.  OMR_OUT_COEFF mitigates SURVEY §8b risk 1 on the
+ * output side: the Rust shim re-transforms with Primus-fhe's own NTT table (NttRlwe <-> Rlwe), so nothing depends on the two
+ * libraries agreeing on the root of unity or on the output ordering.  Device-pointer calls are always NTT-native. */
+#define OMR_OUT_NTT_NATIVE 0u
+#define OMR_OUT_COEFF 1u
 
 /* Replaces DetectionKey (omr_core/src/key_gen/detection.rs:9-16) flattened:
  *   BlindRotationKey<F1> -> bsk1, NonPowOf2LweKeySwitchingKey -> ksk, BlindRotationKey<F2> -> bsk2,
@@ -83,12 +93,19 @@ typedef struct omr_ctx omr_ctx;
 /* ---- lifetime -------------------------------------------------------------------------------------------- */
 /* Replaces Detector::new(DetectionKey) (detector.rs:85-110): uploads and owns device copies of the keys. */
 int omr_ctx_create(int device, const omr_key_blobs* keys, omr_ctx** out);
-/* Keys already resident on `device` (same layouts); copied once more into the context's internal form. */
+/* Keys already resident on `device` (same layouts); copied once more into the context's internal form.  The call drains the
+ * device (cudaDeviceSynchronize) before the first copy, so the key tensors may have been produced on any stream. */
 int omr_ctx_create_device_keys(int device, const omr_key_blobs* device_keys, omr_ctx** out);
 void omr_ctx_destroy(omr_ctx* ctx);
 const char* omr_last_error(const omr_ctx* ctx); /* NULL ctx -> error of the last failed create */
 /* Detector::detect_key_size (detector.rs:112-114): bytes of key material resident on the device */
 size_t omr_detect_key_size(const omr_ctx* ctx);
+/* Detector::first_level_lut / second_level_lut (detector.rs:117-132; built at :457-503 with lut.rs:12-27): the two test vectors
+ * in coefficient form, copied to the host. */
+int omr_first_level_lut(const omr_ctx* ctx, uint32_t* out /*[1024] mod q1*/);
+int omr_second_level_lut(const omr_ctx* ctx, uint64_t* out /*[2048] mod q2*/);
+/* OMR_OUT_NTT_NATIVE (default) or OMR_OUT_COEFF for every later host-buffer call on this context. */
+int omr_set_output_domain(omr_ctx* ctx, uint32_t domain);
 /* RetrievalParams::new(257, 2048, D, k, 130, 25, 2) — secret.rs:189-209 */
 int omr_retrieval_params_init(uint64_t all_payloads_count, uint32_t pertinent_count, omr_retrieval_params* out);
 
@@ -109,10 +126,11 @@ int omr_pv_reset(omr_ctx* ctx);
 int omr_encode_indices(omr_ctx* ctx, const omr_retrieval_params* rp, uint64_t seed, uint32_t cipher_idx0,
                        uint32_t n_cipher, uint64_t* out);
 /* Replaces Detector::encode_pertinent_payloads (detector.rs:341-453).  payloads [count][612] for the messages in
- * the store (count must equal the store size, global indices index0..), weights [rows][weight_stride] row-major
+ * the store (count must equal the store size, global indices index0..), weights [weight_rows][weight_stride] row-major
  * u16 in [0,257) with column = GLOBAL message index (the caller draws them: StdRng + Uniform, detector.rs:376-387),
- * rows >= n_cipher*cmb_per_cipher.  out [n_cipher][2][2048]. */
-int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, const uint16_t* weights,
+ * 1 <= weight_rows <= n_cipher*cmb_per_cipher; rows beyond weight_rows count as zero (the reference allocates
+ * ceil(cc / per) * per rows and fills combination_count of them, detector.rs:370-387).  out [n_cipher][2][2048]. */
+int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, const uint16_t* weights, size_t weight_rows,
                         size_t weight_stride, uint32_t n_cipher, uint32_t cmb_per_cipher, uint64_t* out);
 
 /* ---- device-pointer forms (inputs already in HBM; `stream` is a cudaStream_t, NULL = the default stream) -------------------------- */
@@ -147,7 +165,7 @@ int omr_decrypt_decode_device(omr_ctx* ctx, const uint64_t* d_z2_ntt /*[2048]*/,
  * system mod 257 (solve_matrix_mod_257, matrix.rs:164-247).  indices_out [pertinent_count] (sorted), *n_found, payloads_out
  * [pertinent_count][612].  A singular system returns OMR_ERR_INVALID with "matrix is not invertible" (OmrError::
  * InvertibleMatrix, error.rs:4-8). */
-int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* z2_ntt /*[2048]*/,
+int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* z2 /*[2048]: NTT(z2), or z2 mod q2 in coefficient form under OMR_OUT_COEFF (like the ciphertexts)*/,
                       const uint64_t* index_cts /*[n_index_cts][2][2048]*/, uint32_t n_index_cts,
                       const uint64_t* payload_cts /*[n_payload_cts][2][2048]*/, uint32_t n_payload_cts,
                       const uint16_t* weights, size_t weight_stride,
@@ -168,9 +186,11 @@ int omr_encode_payloads_seeded(omr_ctx* ctx, const uint16_t* payloads, size_t co
 
 /* Sender side (Sender::gen_clues -> ClueKey::gen_clues, sender.rs:27-30, key_gen/clue.rs:27-34): `count` clues
  * under the clue public key (pa, pb) [512] u16 each, for global message indices index0.., encrypting d_msgs[i][7] (values
- * mod 8; NULL = seven 0's as the reference does).  Randomness is a counter hash of (seed, message index), see DESIGN.md.
+ * mod 8; NULL = seven 0's as the reference does).  The reference takes `R: Rng + CryptoRng`; here every draw (the binary mask
+ * r, the errors e1, e2) comes from ChaCha12 keyed by seed32 (host pointer, 32 bytes from the caller's CSPRNG) in counter mode
+ * over (message index, domain, block) — see kernels.cuh: clue_gen_kernel.  Never reuse a seed for the same index range.
  * d_a [count][512], d_b [count][7]. */
-int omr_gen_clues_device(omr_ctx* ctx, const uint16_t* d_pa, const uint16_t* d_pb, uint64_t seed, uint64_t index0, size_t count,
+int omr_gen_clues_device(omr_ctx* ctx, const uint16_t* d_pa, const uint16_t* d_pb, const uint8_t* seed32, uint64_t index0, size_t count,
                          const uint8_t* d_msgs, uint16_t* d_a, uint16_t* d_b, void* stream);
 
 /* ---- stage entry points (device pointers) — the stage list of benches/two_level_bs.rs:47-145 ------------------- */
@@ -185,6 +205,48 @@ int omr_trace_device(omr_ctx* ctx, uint64_t* d_rlwe /*[B][2][2048], in place -> 
 int omr_ntt_forward_device(omr_ctx* ctx, int level, void* d_data, size_t batch, void* stream);
 int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d_data, size_t batch, void* stream);
 
+/* ---- wire / on-disk format ------------------------------------------------------------------------------------
+ * The reference serialises nothing (only `Size` byte counts: key_gen/detection.rs:81-88, sender.rs:36); these versioned flat
+ * little-endian blobs are what the Rust shim (ffi/omr-b200-sys), the CPU oracle, tfhe_omr_b200.blobs (Python) and this library
+ * exchange.  File = 64-byte header ("OMRB200\0", then the fields of omr_blob_header in order) + the arrays of the kind, in the
+ * order below, C-contiguous.  `domain` says how ring polynomials are stored (OMR_OUT_NTT_NATIVE / OMR_OUT_COEFF).
+ *   1 detection_key      bsk1 u32[512][8][2][1024], ksk u32[1024][27][671], bsk2 u64[670][12][2][2048], trace u64[11][25][2][2048]
+ *   2 clues              a u16[count][512], b u16[count][7]                    (CmLweCiphertext<u16> x count)
+ *   3 pertinency_vector  pv u64[count][2][2048]                                (NttRlweCiphertext<F2> x count, index0 = first global index)
+ *   4 digest             ct u64[count][2][2048]                                (aux = number of index ciphertexts, the rest are payload ciphertexts)
+ *   5 payloads           payloads u16[count][612]
+ *   6 secret_key         s0 i32[512], z1 i32[1024], s2 i32[670], z2 i32[2048]  (test vectors only)
+ *   7 rlwe1              ct u32[count][2][1024]   sum of the 7 first-level accumulators (detector.rs:556), coefficient form
+ *   8 lwe2               ct u32[count][671]       after key switch, modulus switch and offset (detector.rs:560-596)
+ *   9 rlwe2              ct u64[count][2][2048]   after the second-level blind rotation (detector.rs:623), coefficient form
+ *  10 clue_key           pa u16[512], pb u16[512]
+ * Errors of these context-free calls are reported through omr_last_error(NULL). */
+#define OMR_BLOB_VERSION 1u
+#define OMR_BLOB_DETECTION_KEY 1u
+#define OMR_BLOB_CLUES 2u
+#define OMR_BLOB_PERTINENCY_VECTOR 3u
+#define OMR_BLOB_DIGEST 4u
+#define OMR_BLOB_PAYLOADS 5u
+#define OMR_BLOB_SECRET_KEY 6u
+#define OMR_BLOB_RLWE1 7u
+#define OMR_BLOB_LWE2 8u
+#define OMR_BLOB_RLWE2 9u
+#define OMR_BLOB_CLUE_KEY 10u
+typedef struct {
+    uint32_t version, kind;
+    uint64_t count, index0, aux, payload_bytes;
+    uint32_t domain, reserved[3];
+} omr_blob_header;
+uint32_t omr_blob_field_count(uint32_t kind);                                    /* arrays of a kind (0 = unknown kind) */
+size_t omr_blob_field_bytes(uint32_t kind, uint32_t field, uint64_t count);      /* bytes of array `field` at `count` */
+int omr_blob_write(const char* path, uint32_t kind, uint64_t count, uint64_t index0, uint64_t aux, uint32_t domain,
+                   const void* const* arrays, uint32_t n_arrays);
+int omr_blob_read_header(const char* path, omr_blob_header* hdr);
+/* arrays[i] must hold omr_blob_field_bytes(hdr.kind, i, hdr.count) bytes (read the header first) */
+int omr_blob_read(const char* path, omr_blob_header* hdr /*nullable*/, void* const* arrays, uint32_t n_arrays);
+/* Detector::new (detector.rs:85) from a detection-key blob; its `domain` selects OMR_KEYS_NTT_NATIVE / OMR_KEYS_COEFF */
+int omr_ctx_create_from_blob(int device, const char* path, omr_ctx** out);
+
 /* Step-0 peak: sustained rate of the register-only Shoup butterfly loop the NTTs are made of,
  * level 1 = 32-bit integer (q1), level 2 = 64-bit integer (q2), level 3 = q2 on the FP64 pipe (what the level-2 kernel
  * uses); the denominators of the compute roofline in bench.py. */
@@ -196,11 +258,13 @@ int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_seco
  * the throughput shapes.  Both give bit-identical results; enable = 0 forces the throughput shapes for every batch size. */
 int omr_set_latency_shapes(omr_ctx* ctx, int enable);
 
-/* Key switch on the tensor cores.  The LWE key switch (detector.rs:560-563) is a {-1,0,1} x u32 matrix product; when the
- * library was built with the CUTLASS headers it runs as an exact int8 GEMM (tcgen05, int32 accumulation, key split into
- * 8-bit limbs) at every batch size, otherwise — or with enable = 0 — as CUDA-core kernels.  Identical results.  Enabling it
- * on a library built without it returns OMR_ERR_STATE. */
+/* Key switch path.  The LWE key switch (detector.rs:560-563) is a {-1,0,1} x u32 matrix product.  Default: the hand-written
+ * CUDA-core kernels (keyswitch_kernel).  Opt-in (enable = 1, or OMR_KS_GEMM=1 in the environment), when the library was built
+ * with the CUTLASS headers: an exact int8 tensor-core GEMM (a CUTLASS template instance: int32 accumulation, key split into
+ * 8-bit limbs; 74 MB of extra key material built on first use).  Identical results.  Enabling it on a library built without
+ * it returns OMR_ERR_STATE.  omr_key_switch_path: 0 = CUDA cores, 1 = tensor-core GEMM. */
 int omr_set_tensor_core_key_switch(omr_ctx* ctx, int enable);
+int omr_key_switch_path(const omr_ctx* ctx);
 
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
 uint64_t omr_launch_count(const omr_ctx* ctx);

@@ -416,31 +416,42 @@ inline void gen_clue(const ClueKey& k, u64 seed, u64 index, const u32* msgs /*7 
     }
 }
 
-// Counter-based clue generation: the same public-key encryption as gen_clue, but every random draw is a
-// hash of (seed, message index, domain, position) and the rounded Gaussian (sigma = 0.8293, parameters/mod.rs:45) comes
-// from an integer cumulative table, so the CUDA kernel (csrc: clue_gen_kernel) reproduces it bit for bit (no libm).
+// Counter-based clue generation: the same public-key encryption as gen_clue, but every random draw comes from
+// ChaCha12 keyed by a 32-byte seed in counter mode (the reference requires a CryptoRng here: key_gen/clue.rs:27-30) —
+// block(counter = message index, nonce = (domain, block)): domain 1 = the 512 bits of r, domain 2 = e1 (one u64 per draw, 8 per
+// block), domain 3 = e2 — and the rounded Gaussian (sigma = 0.8293, parameters/mod.rs:45) comes from an integer cumulative
+// table, so the CUDA kernel (csrc: clue_gen_kernel) reproduces it bit for bit (no libm).
 //   P(|e| <= k) * 2^32 for k = 0..4, sigma = 0.8293 (tail beyond 5 is < 2^-32)
 static const u32 CLUE_CDT[5] = {1947496405u, 3992218608u, 4283915214u, 4294862567u, 4294967049u};
-inline u64 mix64_(u64 z) { z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
-inline u64 clue_hash(u64 seed, u64 index, u32 domain, u32 pos) {
-    return mix64_(mix64_(seed + 0x9E3779B97F4A7C15ull * (index + 1)) ^ ((((u64)domain << 32) | pos) * 0xD1342543DE82EF95ull));
+inline void chacha_block(const u32 key[8], u64 counter, u64 stream, int rounds, u32 out[16]);
+inline void seed_to_key(const u8 seed[32], u32 key[8]) {
+    for (int i = 0; i < 8; ++i) key[i] = (u32)seed[4 * i] | ((u32)seed[4 * i + 1] << 8) | ((u32)seed[4 * i + 2] << 16) | ((u32)seed[4 * i + 3] << 24);
 }
 inline i32 clue_gauss(u64 h) {
     const u32 u = (u32)h; i32 m = 0;
     for (int k = 0; k < 5; ++k) m += u >= CLUE_CDT[k];
     return (h >> 63) ? -m : m;
 }
-inline void gen_clue_cb(const ClueKey& k, u64 seed, u64 index, const u8* msgs /*7 values mod 8 or null*/, u16* a_out, u16* b_out) {
+inline void gen_clue_cb(const ClueKey& k, const u8 seed[32], u64 index, const u8* msgs /*7 values mod 8 or null*/, u16* a_out, u16* b_out) {
+    u32 key[8]; seed_to_key(seed, key);
+    u32 w[16];
     std::vector<i32> rr(CLUE_N);
-    for (int j = 0; j < CLUE_N; ++j) rr[j] = (i32)(clue_hash(seed, index, 0, (u32)j) & 1);
+    chacha_block(key, index, 1ull, 12, w);
+    for (int j = 0; j < CLUE_N; ++j) rr[j] = (i32)((w[j / 32] >> (j % 32)) & 1u);
     std::vector<u16> u(CLUE_N), v(CLUE_N);
     negacyclic_mul_small(k.pa.data(), rr.data(), CLUE_N, CLUE_Q - 1, u.data());
     negacyclic_mul_small(k.pb.data(), rr.data(), CLUE_N, CLUE_Q - 1, v.data());
-    for (int i = 0; i < CLUE_N; ++i) a_out[i] = (u16)(((i64)u[i] + clue_gauss(clue_hash(seed, index, 1, (u32)i))) & (CLUE_Q - 1));
+    for (int i = 0; i < CLUE_N; ++i) {
+        if (i % 8 == 0) chacha_block(key, index, 2ull | ((u64)(i / 8) << 32), 12, w);
+        const u64 h = (u64)w[2 * (i % 8)] | ((u64)w[2 * (i % 8) + 1] << 32);
+        a_out[i] = (u16)(((i64)u[i] + clue_gauss(h)) & (CLUE_Q - 1));
+    }
+    chacha_block(key, index, 3ull, 12, w);
     const u32 delta = CLUE_Q / CLUE_T;
     for (int c = 0; c < CLUE_COUNT; ++c) {
         const i64 m = msgs ? (i64)(msgs[c] % CLUE_T) * delta : 0;
-        b_out[c] = (u16)(((i64)v[c] + clue_gauss(clue_hash(seed, index, 2, (u32)c)) + m) & (CLUE_Q - 1));
+        const u64 h = (u64)w[2 * c] | ((u64)w[2 * c + 1] << 32);
+        b_out[c] = (u16)(((i64)v[c] + clue_gauss(h) + m) & (CLUE_Q - 1));
     }
 }
 

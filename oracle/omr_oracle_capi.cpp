@@ -1,6 +1,7 @@
 // extern "C" surface of the CPU oracle (ctypes-loadable).  TEST INFRASTRUCTURE ONLY — see omr_oracle.hpp.
 // PARITY UNPINNED against Primus-fhe (see header of omr_oracle.hpp).
 #include "omr_oracle.hpp"
+#include <cstdio>
 #include <thread>
 #include <atomic>
 #include <string>
@@ -107,7 +108,7 @@ void orc_gen_clues(void* hh, uint64_t seed, uint64_t index0, size_t count, uint1
     parallel_for((size_t)count, threads, [&](size_t i) { gen_clue(h->ck, seed, index0 + i, nullptr, a + i * CLUE_N, b + i * CLUE_COUNT); });
 }
 // counter-based variant (bit-exact twin of the CUDA clue_gen_kernel)
-void orc_gen_clues_cb(void* hh, uint64_t seed, uint64_t index0, size_t count, const uint8_t* msgs /*nullable [count][7]*/, uint16_t* a, uint16_t* b, int threads) {
+void orc_gen_clues_cb(void* hh, const uint8_t* seed /*32 bytes*/, uint64_t index0, size_t count, const uint8_t* msgs /*nullable [count][7]*/, uint16_t* a, uint16_t* b, int threads) {
     auto* h = (OrcHandle*)hh;
     parallel_for((size_t)count, threads, [&](size_t i) { gen_clue_cb(h->ck, seed, index0 + i, msgs ? msgs + i * CLUE_COUNT : nullptr, a + i * CLUE_N, b + i * CLUE_COUNT); });
 }
@@ -214,6 +215,41 @@ uint32_t orc_phase_lwe2(void* hh, const uint32_t* lwe /*[671] mod 4096*/) {
     auto* h = (OrcHandle*)hh; i64 ph = lwe[LWE2_N];
     for (int i = 0; i < LWE2_N; ++i) ph -= (i64)lwe[i] * h->sk.s2[i];
     return (u32)(ph & (LWE2_Q - 1));
+}
+
+
+// ---- blobs: the oracle's own reader/writer of the OMRB200 container ------------------------------------------
+// header: "OMRB200\0" u32 version u32 kind u64 count u64 index0 u64 aux u64 payload_bytes u32 domain 12 reserved; then raw arrays.
+// The oracle does not know the kinds: it moves the payload as one byte string (the tests slice it), which is enough to check
+// that the three implementations (Python, CUDA library, oracle) agree on the container.
+// returns 0 ok; 1 cannot open / short; 2 bad magic / version / size
+int orc_blob_read(const char* path, uint64_t* hdr /*[8]: version kind count index0 aux payload_bytes domain 0*/, uint8_t* payload, uint64_t payload_cap) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return 1;
+    unsigned char raw[64];
+    if (std::fread(raw, 1, 64, f) != 64) { std::fclose(f); return 1; }
+    if (std::memcmp(raw, "OMRB200\0", 8) != 0) { std::fclose(f); return 2; }
+    auto rd = [&](int off, int n) { uint64_t v = 0; for (int i = 0; i < n; ++i) v |= (uint64_t)raw[off + i] << (8 * i); return v; };
+    hdr[0] = rd(8, 4); hdr[1] = rd(12, 4); hdr[2] = rd(16, 8); hdr[3] = rd(24, 8); hdr[4] = rd(32, 8); hdr[5] = rd(40, 8); hdr[6] = rd(48, 4); hdr[7] = 0;
+    if (hdr[0] != 1) { std::fclose(f); return 2; }
+    int st = 0;
+    if (payload) {
+        if (hdr[5] > payload_cap) st = 2;
+        else if (std::fread(payload, 1, hdr[5], f) != hdr[5]) st = 1;
+        else if (std::fgetc(f) != EOF) st = 2;
+    }
+    std::fclose(f);
+    return st;
+}
+int orc_blob_write(const char* path, uint32_t kind, uint64_t count, uint64_t index0, uint64_t aux, uint32_t domain, const uint8_t* payload, uint64_t payload_bytes) {
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return 1;
+    unsigned char raw[64] = {0};
+    std::memcpy(raw, "OMRB200\0", 8);
+    auto wr = [&](int off, int n, uint64_t v) { for (int i = 0; i < n; ++i) raw[off + i] = (unsigned char)(v >> (8 * i)); };
+    wr(8, 4, 1); wr(12, 4, kind); wr(16, 8, count); wr(24, 8, index0); wr(32, 8, aux); wr(40, 8, payload_bytes); wr(48, 4, domain);
+    bool ok = std::fwrite(raw, 1, 64, f) == 64 && std::fwrite(payload, 1, payload_bytes, f) == payload_bytes;
+    return (std::fclose(f) == 0 && ok) ? 0 : 1;
 }
 
 }  // extern "C"

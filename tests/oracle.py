@@ -56,7 +56,7 @@ def lib(native=False):
     L.orc_secret.argtypes = [vp, vp, vp, vp, vp]
     L.orc_gen_clues.argtypes = [vp, u64, u64, sz, vp, vp, i32]
     L.orc_gen_clue_msgs.argtypes = [vp, u64, u64, vp, vp, vp]
-    L.orc_gen_clues_cb.argtypes = [vp, u64, u64, sz, vp, vp, vp, i32]
+    L.orc_gen_clues_cb.argtypes = [vp, C.c_char_p, u64, sz, vp, vp, vp, i32]
     L.orc_clue_key.argtypes = [vp, vp, vp]
     L.orc_decrypt_clue.argtypes = [vp, vp, vp, vp]
     L.orc_detect.argtypes = [vp, vp, vp, sz, vp, i32]
@@ -88,6 +88,8 @@ def lib(native=False):
     L.orc_retrieval_params.argtypes = [sz, i32, vp]
     L.orc_lut1.argtypes = [vp]; L.orc_lut2.argtypes = [vp]
     L.orc_twiddles1.argtypes = [vp, vp]; L.orc_twiddles2.argtypes = [vp, vp]
+    L.orc_blob_read.restype = i32; L.orc_blob_read.argtypes = [C.c_char_p, vp, vp, u64]
+    L.orc_blob_write.restype = i32; L.orc_blob_write.argtypes = [C.c_char_p, u32, u64, u64, u64, u32, vp, u64]
     L.orc_inv_mod_257.restype = C.c_uint16; L.orc_inv_mod_257.argtypes = [i32]
     _lib_cache[native] = L
     return L
@@ -148,7 +150,10 @@ class KeyPack:
         return a, b
 
     def gen_clues_cb(self, seed, count, index0=0, msgs=None, threads=8):
-        """counter-based clue generation (bit-exact twin of the CUDA clue_gen_kernel)"""
+        """counter-based clue generation (bit-exact twin of the CUDA clue_gen_kernel); seed = 32 bytes (an int is widened
+        little-endian)"""
+        seed = seed.to_bytes(32, "little") if isinstance(seed, int) else bytes(seed)
+        assert len(seed) == 32
         a = np.zeros((count, CLUE_N), np.uint16); b = np.zeros((count, CLUE_COUNT), np.uint16)
         m = None if msgs is None else np.ascontiguousarray(msgs, np.uint8).reshape(count, CLUE_COUNT)
         self.L.orc_gen_clues_cb(self.h, seed, index0, count, None if m is None else ptr(m), ptr(a), ptr(b), threads)

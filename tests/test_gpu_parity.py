@@ -171,8 +171,8 @@ def test_weights_from_seed_match_reference_stream(detector):
 
 
 def test_tensor_core_key_switch_is_exact(detector, keypack):
-    """The key switch runs as an int8 tensor-core GEMM (digits x key limbs, int32 accumulation, limbs recombined mod q1).
-    Its words must equal the CUDA-core kernels' (split rows for <= 256 messages, one CTA per 16 messages above) on
+    """The opt-in tensor-core key switch (digits x key limbs as an int8 GEMM, int32 accumulation, limbs recombined mod q1):
+    its words must equal the default CUDA-core kernels' (split rows for <= 256 messages, one CTA per 16 messages above) on
     full-range random ciphertexts at ragged batch sizes, and the oracle's on a sample — including saturated rows."""
     import torch
     rng = np.random.default_rng(21)
@@ -180,13 +180,14 @@ def test_tensor_core_key_switch_is_exact(detector, keypack):
     rl[5] = O.Q1 - 1; rl[6] = 0; rl[7, 0] = (O.Q1 - 1) // 2; rl[8, 0] = (O.Q1 + 1) // 2      # extreme digits: all -1 / 0 / +-max
     d = _dev(rl, np.int32)
     sizes = (1, 9, 256, 257, 1030)
-    detector.set_tensor_core_key_switch(True)
-    tc = [detector.key_switch(d[:n]) for n in sizes]; torch.cuda.synchronize()
+    assert detector.key_switch_path() == "cuda-core"                                        # the hand-written kernels are the default
+    cc = [detector.key_switch(d[:n]) for n in sizes]; torch.cuda.synchronize()
     try:
-        detector.set_tensor_core_key_switch(False)
-        cc = [detector.key_switch(d[:n]) for n in sizes]; torch.cuda.synchronize()
+        detector.set_tensor_core_key_switch(True)                                           # opt-in CUTLASS int8 GEMM
+        assert detector.key_switch_path() == "tensor-core"
+        tc = [detector.key_switch(d[:n]) for n in sizes]; torch.cuda.synchronize()
     finally:
-        detector.set_tensor_core_key_switch(True)
+        detector.set_tensor_core_key_switch(False)
     for x, y in zip(tc, cc):
         assert torch.equal(x, y)
     sample = np.array([0, 5, 6, 7, 8, 511, 1023, 1029])

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libomr_b200.so")
 
 OMR_OK, OMR_ERR_INVALID, OMR_ERR_CUDA, OMR_ERR_ALLOC, OMR_ERR_STATE = range(5)
 KEYS_NTT_NATIVE, KEYS_COEFF = 0, 1
+OUT_NTT_NATIVE, OUT_COEFF = 0, 1
 
 # every symbol include/omr_b200.h declares (tests check the library exports each of them)
 EXPORTS = [
@@ -16,6 +17,8 @@ EXPORTS = [
     "omr_detect_batch_device", "omr_encode_indices_device", "omr_encode_payloads_device", "omr_digest_reduce_mod",
     "omr_l1_blind_rotate_device", "omr_keyswitch_device", "omr_l2_blind_rotate_device", "omr_trace_device",
     "omr_ntt_forward_device", "omr_ntt_inverse_device", "omr_launch_count", "omr_mulmod_peak", "omr_digest_add_mod", "omr_decrypt_decode_device", "omr_gen_clues_device", "omr_set_latency_shapes", "omr_decode_digest", "omr_weights_from_seed_device", "omr_encode_payloads_seeded", "omr_set_tensor_core_key_switch",
+    "omr_blob_field_count", "omr_blob_field_bytes", "omr_blob_write", "omr_blob_read_header", "omr_blob_read", "omr_ctx_create_from_blob",
+    "omr_first_level_lut", "omr_second_level_lut", "omr_set_output_domain", "omr_key_switch_path",
 ]
 
 
@@ -26,6 +29,11 @@ class KeyBlobs(C.Structure):
 class StageTimes(C.Structure):
     _fields_ = [("detect_ms", C.c_float), ("first_level_bootstrapping_ms", C.c_float),
                 ("second_level_bootstrapping_ms", C.c_float), ("trace_ms", C.c_float)]
+
+
+class BlobHeader(C.Structure):
+    _fields_ = [("version", C.c_uint32), ("kind", C.c_uint32), ("count", C.c_uint64), ("index0", C.c_uint64), ("aux", C.c_uint64),
+                ("payload_bytes", C.c_uint64), ("domain", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class RetrievalParamsC(C.Structure):
@@ -64,7 +72,7 @@ def load():
     L.omr_detect_batch.restype = i32; L.omr_detect_batch.argtypes = [vp, vp, vp, sz, u64, vp, P(StageTimes)]
     L.omr_pv_reset.restype = i32; L.omr_pv_reset.argtypes = [vp]
     L.omr_encode_indices.restype = i32; L.omr_encode_indices.argtypes = [vp, P(RetrievalParamsC), u64, u32, u32, vp]
-    L.omr_encode_payloads.restype = i32; L.omr_encode_payloads.argtypes = [vp, vp, sz, vp, sz, u32, u32, vp]
+    L.omr_encode_payloads.restype = i32; L.omr_encode_payloads.argtypes = [vp, vp, sz, vp, sz, sz, u32, u32, vp]
     L.omr_detect_batch_device.restype = i32; L.omr_detect_batch_device.argtypes = [vp, vp, vp, sz, vp, vp, P(StageTimes)]
     L.omr_encode_indices_device.restype = i32
     L.omr_encode_indices_device.argtypes = [vp, P(RetrievalParamsC), vp, sz, u64, u64, u32, u32, vp, vp]
@@ -79,7 +87,17 @@ def load():
     L.omr_ntt_inverse_device.restype = i32; L.omr_ntt_inverse_device.argtypes = [vp, i32, vp, sz, vp]
     L.omr_digest_add_mod.restype = i32; L.omr_digest_add_mod.argtypes = [vp, vp, vp, sz, vp]
     L.omr_decrypt_decode_device.restype = i32; L.omr_decrypt_decode_device.argtypes = [vp, vp, vp, sz, vp, vp]
-    L.omr_gen_clues_device.restype = i32; L.omr_gen_clues_device.argtypes = [vp, vp, vp, u64, u64, sz, vp, vp, vp, vp]
+    L.omr_gen_clues_device.restype = i32; L.omr_gen_clues_device.argtypes = [vp, vp, vp, C.c_char_p, u64, sz, vp, vp, vp, vp]
+    L.omr_blob_field_count.restype = u32; L.omr_blob_field_count.argtypes = [u32]
+    L.omr_blob_field_bytes.restype = sz; L.omr_blob_field_bytes.argtypes = [u32, u32, u64]
+    L.omr_blob_write.restype = i32; L.omr_blob_write.argtypes = [C.c_char_p, u32, u64, u64, u64, u32, P(vp), u32]
+    L.omr_blob_read_header.restype = i32; L.omr_blob_read_header.argtypes = [C.c_char_p, P(BlobHeader)]
+    L.omr_blob_read.restype = i32; L.omr_blob_read.argtypes = [C.c_char_p, P(BlobHeader), P(vp), u32]
+    L.omr_ctx_create_from_blob.restype = i32; L.omr_ctx_create_from_blob.argtypes = [i32, C.c_char_p, P(vp)]
+    L.omr_first_level_lut.restype = i32; L.omr_first_level_lut.argtypes = [vp, vp]
+    L.omr_second_level_lut.restype = i32; L.omr_second_level_lut.argtypes = [vp, vp]
+    L.omr_set_output_domain.restype = i32; L.omr_set_output_domain.argtypes = [vp, u32]
+    L.omr_key_switch_path.restype = i32; L.omr_key_switch_path.argtypes = [vp]
     L.omr_mulmod_peak.restype = i32; L.omr_mulmod_peak.argtypes = [vp, i32, i32, P(C.c_double)]
     _lib = L
     return L

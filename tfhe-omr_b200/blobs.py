@@ -4,8 +4,12 @@ The reference serialises nothing (it only reports byte counts through `Size`: ke
 these little-endian containers let the Rust shim, the oracle and the GPU library exchange keys, clues, pertinency vectors
 and digests, and make runs replayable.  Layouts are exactly the arrays of include/omr_b200.h.
 
-    header (64 bytes): magic b"OMRB200\\0" | u32 version | u32 kind | u64 count | u64 index0 | u64 aux | u64 payload bytes | 16 B reserved
+    header (64 bytes): magic b"OMRB200\\0" | u32 version | u32 kind | u64 count | u64 index0 | u64 aux | u64 payload bytes |
+                       u32 domain (0 = this library's NTT ordering, 1 = coefficient form) | 12 B reserved
     payload: the arrays of the kind, in the order listed in KINDS, C-contiguous, little-endian
+
+The same container is read and written by libomr_b200.so (csrc/blob.cu: omr_blob_read / omr_blob_write /
+omr_ctx_create_from_blob) and by the CPU restatement used as test infrastructure; tests/test_blobs.py cross-checks the three.
 """
 import struct
 
@@ -13,7 +17,8 @@ import numpy as np
 
 MAGIC = b"OMRB200\0"
 VERSION = 1
-_HDR = struct.Struct("<8sIIQQQQ16x")
+_HDR = struct.Struct("<8sIIQQQQI12x")
+DOMAIN_NTT_NATIVE, DOMAIN_COEFF = 0, 1
 
 # kind -> (name, [(field, dtype, shape with -1 = count)])
 KINDS = {
@@ -23,11 +28,16 @@ KINDS = {
     3: ("pertinency_vector", [("pv", np.uint64, (-1, 2, 2048))]),                                              # NttRlweCiphertext<F2> x count
     4: ("digest", [("ct", np.uint64, (-1, 2, 2048))]),                                                         # aux: number of index ciphertexts
     5: ("payloads", [("payloads", np.uint16, (-1, 612))]),
+    6: ("secret_key", [("s0", np.int32, (512,)), ("z1", np.int32, (1024,)), ("s2", np.int32, (670,)), ("z2", np.int32, (2048,))]),   # test vectors only
+    7: ("rlwe1", [("ct", np.uint32, (-1, 2, 1024))]),                                                          # sum of the 7 L1 accumulators (detector.rs:556)
+    8: ("lwe2", [("ct", np.uint32, (-1, 671))]),                                                               # after KS + mod switch + offset (detector.rs:560-596)
+    9: ("rlwe2", [("ct", np.uint64, (-1, 2, 2048))]),                                                          # after the L2 blind rotation (detector.rs:623)
+    10: ("clue_key", [("pa", np.uint16, (512,)), ("pb", np.uint16, (512,))]),
 }
 _BY_NAME = {v[0]: k for k, v in KINDS.items()}
 
 
-def dump(path, kind, arrays, count=0, index0=0, aux=0):
+def dump(path, kind, arrays, count=0, index0=0, aux=0, domain=DOMAIN_NTT_NATIVE):
     """Write one blob.  `arrays` maps field name -> array."""
     kid = _BY_NAME[kind]
     fields = KINDS[kid][1]
@@ -40,7 +50,7 @@ def dump(path, kind, arrays, count=0, index0=0, aux=0):
         parts.append(arr)
     nbytes = sum(p.nbytes for p in parts)
     with open(path, "wb") as f:
-        f.write(_HDR.pack(MAGIC, VERSION, kid, count, index0, aux, nbytes))
+        f.write(_HDR.pack(MAGIC, VERSION, kid, count, index0, aux, nbytes, domain))
         for p in parts:
             f.write(p.tobytes())
 
@@ -51,7 +61,7 @@ def load(path, mmap=False):
         hdr = f.read(_HDR.size)
         if len(hdr) != _HDR.size:
             raise ValueError("truncated header")
-        magic, version, kid, count, index0, aux, nbytes = _HDR.unpack(hdr)
+        magic, version, kid, count, index0, aux, nbytes, domain = _HDR.unpack(hdr)
         if magic != MAGIC:
             raise ValueError("not an OMRB200 blob")
         if version != VERSION:
@@ -74,4 +84,7 @@ def load(path, mmap=False):
             off += n
         if off - _HDR.size != nbytes:
             raise ValueError("payload size mismatch")
-    return name, out, {"version": version, "count": count, "index0": index0, "aux": aux}
+        f.seek(0, 2)
+        if f.tell() != off:
+            raise ValueError("trailing bytes after the payload")
+    return name, out, {"version": version, "count": count, "index0": index0, "aux": aux, "domain": domain}

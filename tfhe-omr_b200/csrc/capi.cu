@@ -60,7 +60,8 @@ struct omr_ctx {
     uint2 n1_inv{}; ulonglong2 n2_inv{};
     size_t key_bytes = 0;
     // scratch for the batched pipeline, sized for `cap` messages
-    size_t cap = 0; u32* s_rlwe1 = nullptr; u32* s_lwe2 = nullptr; unsigned short *s_ca = nullptr, *s_cb = nullptr;
+    size_t cap = 0; u32* s_rlwe1 = nullptr; u32* s_lwe2 = nullptr;
+    size_t clue_cap = 0; unsigned short *s_ca = nullptr, *s_cb = nullptr;   // staged clues of a host-buffer call
     size_t cap7 = 0; u32* s_rlwe7 = nullptr;      // per-(message, clue) accumulators of the L1 kernel
     int l2c_max_clusters = 0;                     // co-resident 6-CTA clusters (cudaOccupancyMaxActiveClusters)
     // tensor-core key switch (large batches): key limbs [KSG_N][KSG_K] int8, per-chunk digits / products / CUTLASS workspace
@@ -79,17 +80,35 @@ struct omr_ctx {
     uint64_t launches = 0;
     int n_sm = 148;
     bool latency_shapes = true;                   // omr_set_latency_shapes / OMR_LATENCY_SHAPES=0: throughput shapes for every batch size
-    // two-stream software pipeline of detect_device
+    uint32_t out_domain = OMR_OUT_NTT_NATIVE;     // omr_set_output_domain: domain of host-buffer ciphertexts
+    u64* s_coeff = nullptr; size_t coeff_words = 0;   // staging for coefficient-domain copies of pertinency ciphertexts
+    std::vector<u32> h_lut1; std::vector<u64> h_lut2; // host copies of the test vectors (omr_first_level_lut / omr_second_level_lut)
 };
 
-namespace omr {            // ks_gemm.cu: the key switch as a tcgen05 int8 GEMM (CUTLASS collective), if it was compiled in
+namespace omr {            // ks_gemm.cu: the key switch as an int8 tensor-core GEMM (a CUTLASS template instance; opt-in), if it was compiled in
 int ks_gemm_i8(const int8_t* A, const int8_t* B, int32_t* C, int M, int N, int K, void* workspace, size_t workspace_bytes, cudaStream_t s);
 size_t ks_gemm_workspace(int M, int N, int K);
 bool ks_gemm_available();
 }
 
+namespace omr { void set_global_error(const std::string& m) { g_create_error = m; } }   // blob.cu, nccl.cu: context-free errors
+
 namespace {
 void ctx_fail(omr_ctx* ctx, const std::string& m) { if (ctx) ctx->err = m; else g_create_error = m; }
+
+// Every entry point runs on the context's device and puts the caller's current device back on return: a process that drives
+// several GPUs (torch reads the current device with cudaGetDevice) must not find it changed behind its back.
+struct DeviceGuard {
+    int prev = -1; cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) err = cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete; DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// lock the context, switch to its device
+#define ENTER(ctx) std::lock_guard<std::mutex> lk_((ctx)->mu); DeviceGuard dg_((ctx)->device); CK(dg_.err)
 
 template <class T> int dalloc(omr_ctx* ctx, T** p, size_t n) {
     CK(cudaMalloc((void**)p, n * sizeof(T)));
@@ -98,14 +117,12 @@ template <class T> int dalloc(omr_ctx* ctx, T** p, size_t n) {
 
 int ensure_scratch(omr_ctx* ctx, size_t B) {
     if (B <= ctx->cap) return OMR_OK;
-    cudaFree(ctx->s_rlwe1); cudaFree(ctx->s_lwe2); cudaFree(ctx->s_ca); cudaFree(ctx->s_cb);
-    ctx->s_rlwe1 = nullptr; ctx->s_lwe2 = nullptr; ctx->s_ca = nullptr; ctx->s_cb = nullptr;      // a failed re-allocation must not leave stale pointers
+    cudaFree(ctx->s_rlwe1); cudaFree(ctx->s_lwe2);
+    ctx->s_rlwe1 = nullptr; ctx->s_lwe2 = nullptr;      // a failed re-allocation must not leave stale pointers
     ctx->cap = 0;
     int st;
     if ((st = dalloc(ctx, &ctx->s_rlwe1, B * 2 * F1::N))) return st;
     if ((st = dalloc(ctx, &ctx->s_lwe2, B * LWE2_STRIDE_IN))) return st;
-    if ((st = dalloc(ctx, &ctx->s_ca, B * CLUE_N))) return st;
-    if ((st = dalloc(ctx, &ctx->s_cb, B * CLUE_COUNT))) return st;
     ctx->cap = B;
     return OMR_OK;
 }
@@ -316,7 +333,7 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     ctx->device = device;
     auto fail = [&](int st) { g_create_error = ctx->err; omr_ctx_destroy(ctx); return st; };
 #define CKC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return fail(OMR_ERR_CUDA); } } while (0)
-    CKC(cudaSetDevice(device));
+    DeviceGuard dg(device); CKC(dg.err);
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) CKC(cudaEventCreate(&ev));
     // constants
@@ -352,6 +369,7 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         CKC(upload(&ctx->d_tw2d, t2d.data(), t2d.size() * sizeof(double2)));
         CKC(upload(&ctx->d_itw2d, it2d.data(), it2d.size() * sizeof(double2)));
     }
+    ctx->h_lut1 = lut1; ctx->h_lut2 = lut2;
     CKC(upload(&ctx->d_lut1, lut1.data(), lut1.size() * sizeof(u32)));
     CKC(upload(&ctx->d_lut2, lut2.data(), lut2.size() * sizeof(u64)));
     Tables& tb = ctx->tb;
@@ -416,21 +434,18 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     ctx->key_bytes = n_bsk1 * 4 + n_ksk_rows * KSK_PAD * 4 + n_bsk2 * 8 + n_trk * 8;
     const cudaMemcpyKind kind = keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     cudaStream_t s = ctx->stream;
+    // device-resident keys were produced on some stream of the caller: the context's own (non-blocking) stream has no ordering
+    // against it, so drain the device once before the first copy
+    if (keys_on_device) CKC(cudaDeviceSynchronize());
     {
         u32* tmp = nullptr; CKC(cudaMalloc((void**)&tmp, n_ksk_rows * LWE2_STRIDE_IN * 4));
         CKC(cudaMemcpyAsync(tmp, keys->ksk, n_ksk_rows * LWE2_STRIDE_IN * 4, kind, s));
         ksk_pad_kernel<<<(unsigned)((n_ksk_rows * KSK_PAD + 255) / 256), 256, 0, s>>>(tmp, ctx->ksk, n_ksk_rows); ++ctx->launches;
         CKC(cudaStreamSynchronize(s)); cudaFree(tmp);
     }
-    ctx->ks_gemm = ks_gemm_available();
-    if (const char* e = getenv("OMR_KS_GEMM")) ctx->ks_gemm = ctx->ks_gemm && atoi(e) != 0;
+    // key switch: the hand-written CUDA-core kernels by default; OMR_KS_GEMM=1 or omr_set_tensor_core_key_switch(ctx, 1) opts into
+    // the CUTLASS int8 GEMM (limbs are built then)
     if (const char* e = getenv("OMR_KS_GEMM_MIN")) { long v = atol(e); if (v >= 1) ctx->ksg_min_b = (size_t)v; }
-    if (ctx->ks_gemm) {   // key limbs for the tensor-core key switch: [KSG_N][KSG_K] int8, 74 MB
-        CKC(cudaMalloc((void**)&ctx->ksg_bt, (size_t)KSG_N * KSG_K));
-        CKC(cudaMemsetAsync(ctx->ksg_bt, 0, (size_t)KSG_N * KSG_K, s));
-        ks_limbs_kernel<<<(unsigned)(((size_t)KSG_K * (KSG_N / KSG_LIMBS) + 255) / 256), 256, 0, s>>>(ctx->ksk, ctx->ksg_bt); ++ctx->launches;
-        CKC(cudaStreamSynchronize(s));
-    }
     const bool coeff = keys->flags == OMR_KEYS_COEFF;
     {
         const u32 c1 = h_mulmod<u32>((u32)(((u64)1 << 32) % Q1), n1i, Q1);
@@ -447,6 +462,9 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         CKC(cudaStreamSynchronize(s));
     }
 #undef CKC
+    if (const char* e = getenv("OMR_KS_GEMM")) {
+        if (atoi(e) != 0 && ks_gemm_available()) { const int st = omr_set_tensor_core_key_switch(ctx, 1); if (st) return fail(st); }
+    }
     *out = ctx;
     return OMR_OK;
 }
@@ -460,10 +478,10 @@ int omr_ctx_create_device_keys(int device, const omr_key_blobs* keys, omr_ctx** 
 
 void omr_ctx_destroy(omr_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dg(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
-                    ctx->ks_part, ctx->l2c_scratch, ctx->d_flag, ctx->ksg_bt, ctx->ksg_a, ctx->ksg_c, ctx->ksg_ws, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv};
+                    ctx->ks_part, ctx->l2c_scratch, ctx->d_flag, ctx->ksg_bt, ctx->ksg_a, ctx->ksg_c, ctx->ksg_ws, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv, ctx->s_coeff};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -473,12 +491,37 @@ void omr_ctx_destroy(omr_ctx* ctx) {
 const char* omr_last_error(const omr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 size_t omr_detect_key_size(const omr_ctx* ctx) { return ctx ? ctx->key_bytes : 0; }
 uint64_t omr_launch_count(const omr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int omr_first_level_lut(const omr_ctx* ctx, uint32_t* out) {
+    if (!ctx || !out || ctx->h_lut1.size() != (size_t)OMR_N1) return OMR_ERR_INVALID;
+    memcpy(out, ctx->h_lut1.data(), OMR_N1 * sizeof(uint32_t));
+    return OMR_OK;
+}
+int omr_second_level_lut(const omr_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out || ctx->h_lut2.size() != (size_t)OMR_N2) return OMR_ERR_INVALID;
+    memcpy(out, ctx->h_lut2.data(), OMR_N2 * sizeof(uint64_t));
+    return OMR_OK;
+}
+int omr_set_output_domain(omr_ctx* ctx, uint32_t domain) {
+    if (!ctx || (domain != OMR_OUT_NTT_NATIVE && domain != OMR_OUT_COEFF)) { ctx_fail(ctx, "unknown output domain"); return OMR_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->out_domain = domain;
+    return OMR_OK;
+}
 int omr_set_tensor_core_key_switch(omr_ctx* ctx, int enable) {
     if (!ctx) return OMR_ERR_INVALID;
-    if (enable && !ctx->ksg_bt) { ctx_fail(ctx, "the tensor-core key switch was not built into this library or is disabled (OMR_KS_GEMM=0)"); return OMR_ERR_STATE; }
+    ENTER(ctx);
+    if (enable && !ks_gemm_available()) { ctx_fail(ctx, "the tensor-core key switch was not built into this library"); return OMR_ERR_STATE; }
+    if (enable && !ctx->ksg_bt) {   // key limbs for the tensor-core key switch: [KSG_N][KSG_K] int8, 74 MB, built on first use
+        CK(cudaMalloc((void**)&ctx->ksg_bt, (size_t)KSG_N * KSG_K));
+        CK(cudaMemsetAsync(ctx->ksg_bt, 0, (size_t)KSG_N * KSG_K, ctx->stream));
+        ks_limbs_kernel<<<(unsigned)(((size_t)KSG_K * (KSG_N / KSG_LIMBS) + 255) / 256), 256, 0, ctx->stream>>>(ctx->ksk, ctx->ksg_bt); ++ctx->launches;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->ks_gemm = enable != 0;
     return OMR_OK;
 }
+int omr_key_switch_path(const omr_ctx* ctx) { return ctx && ctx->ks_gemm ? 1 : 0; }
 int omr_set_latency_shapes(omr_ctx* ctx, int enable) {
     if (!ctx) return OMR_ERR_INVALID;
     ctx->latency_shapes = enable != 0;
@@ -500,56 +543,12 @@ int omr_retrieval_params_init(uint64_t all_payloads_count, uint32_t pertinent_co
     return OMR_OK;
 }
 
-// ---- device-pointer forms ----------------------------------------------------------------------------------------------
-int omr_detect_batch_device(omr_ctx* ctx, const uint16_t* d_clue_a, const uint16_t* d_clue_b, size_t B, uint64_t* d_pv, void* stream,
-                            omr_stage_times* times) {
-    if (!ctx || (B && (!d_clue_a || !d_clue_b || !d_pv))) { ctx_fail(ctx, "detect: null argument"); return OMR_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
-    return detect_device(ctx, d_clue_a, d_clue_b, B, (u64*)d_pv, (cudaStream_t)stream, times);
-}
-int omr_l1_blind_rotate_device(omr_ctx* ctx, const uint16_t* a, const uint16_t* b, size_t B, uint32_t* d_rlwe, void* stream) {
-    if (!ctx) return OMR_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    return launch_l1(ctx, a, b, B, d_rlwe, (cudaStream_t)stream);
-}
-int omr_keyswitch_device(omr_ctx* ctx, const uint32_t* d_rlwe, size_t B, uint32_t* d_lwe, void* stream) {
-    if (!ctx) return OMR_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    return launch_ks(ctx, d_rlwe, B, d_lwe, (cudaStream_t)stream);
-}
-int omr_l2_blind_rotate_device(omr_ctx* ctx, const uint32_t* d_lwe, size_t B, uint64_t* d_rlwe, void* stream) {
-    if (!ctx) return OMR_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    return launch_l2(ctx, d_lwe, B, (u64*)d_rlwe, (cudaStream_t)stream);
-}
-int omr_trace_device(omr_ctx* ctx, uint64_t* d_rlwe, size_t B, void* stream) {
-    if (!ctx) return OMR_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    return launch_trace(ctx, (u64*)d_rlwe, B, (cudaStream_t)stream);
-}
-int omr_ntt_forward_device(omr_ctx* ctx, int level, void* d, size_t batch, void* stream) {
-    if (!ctx || (level != 1 && level != 2)) return OMR_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    if (!batch) return OMR_OK;
-    if (level == 1) ntt_kernel<F1, false><<<(unsigned)batch, ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>((u32*)d, ctx->tb, ctx->n1_inv);
-    else ntt_kernel<F2, false><<<(unsigned)batch, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>((u64*)d, ctx->tb, ctx->n2_inv);
-    ++ctx->launches; CK(cudaGetLastError());
-    return OMR_OK;
-}
-int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d, size_t batch, void* stream) {
-    if (!ctx || (level != 1 && level != 2)) return OMR_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    if (!batch) return OMR_OK;
-    if (level == 1) ntt_kernel<F1, true><<<(unsigned)batch, ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>((u32*)d, ctx->tb, ctx->n1_inv);
-    else ntt_kernel<F2, true><<<(unsigned)batch, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>((u64*)d, ctx->tb, ctx->n2_inv);
-    ++ctx->launches; CK(cudaGetLastError());
-    return OMR_OK;
-}
+}  // extern "C"
 
-static int check_rp(omr_ctx* ctx, const omr_retrieval_params* rp) {
+// ---- unlocked implementations (the caller holds ctx->mu and has switched to ctx->device) ---------------------------------
+namespace {
+
+int check_rp(omr_ctx* ctx, const omr_retrieval_params* rp) {
     // encode_pertinent_indices asserts polynomial_size == ntt dimension (detector.rs:236)
     if (!rp || rp->polynomial_size != (uint32_t)OMR_N2 || rp->index_modulus != OMR_P || rp->slots_per_bucket < 2 ||
         rp->slots_per_segment != rp->slots_per_bucket * rp->bucket_count_per_segment ||
@@ -559,30 +558,164 @@ static int check_rp(omr_ctx* ctx, const omr_retrieval_params* rp) {
     return OMR_OK;
 }
 
+int encode_indices_impl(omr_ctx* ctx, const omr_retrieval_params* rp, const u64* d_pv, size_t count, u64 index0, u64 seed, uint32_t cipher_idx0,
+                        uint32_t n_cipher, u64* d_out, cudaStream_t s) {
+    int st; if ((st = check_rp(ctx, rp))) return st;
+    PackIndexArgs ia{rp->slots_per_bucket, rp->slots_per_segment, rp->segment_per_cipher, rp->bucket_count_per_segment, seed, cipher_idx0};
+    return pack_device(ctx, true, d_pv, count, index0, ia, PackPayloadArgs{}, n_cipher, d_out, s);
+}
+int encode_payloads_impl(omr_ctx* ctx, const u64* d_pv, const unsigned short* d_payloads, size_t count, u64 index0, const unsigned short* d_weights,
+                         size_t weight_stride, uint32_t n_cipher, uint32_t cmb_per_cipher, u64* d_out, cudaStream_t s) {
+    if (cmb_per_cipher == 0 || cmb_per_cipher * OMR_PAYLOAD_LEN > OMR_N2 || index0 + count > weight_stride) {
+        ctx_fail(ctx, "encode_payloads: bad combination layout"); return OMR_ERR_INVALID;
+    }
+    PackPayloadArgs pa{d_payloads, d_weights, weight_stride, cmb_per_cipher};
+    return pack_device(ctx, false, d_pv, count, index0, PackIndexArgs{}, pa, n_cipher, d_out, s);
+}
+int weights_from_seed_impl(omr_ctx* ctx, const uint8_t* seed32, size_t count, unsigned short* d_out, uint32_t flags, cudaStream_t s) {
+    if (!count) return OMR_OK;
+    if (!ctx->d_flag) CK(cudaMalloc((void**)&ctx->d_flag, sizeof(int)));
+    const ChaChaKey key = chacha_key_from_seed(seed32);
+    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
+    const size_t blocks = (count + 15) / 16;
+    weights_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, s>>>(key, count, d_out, ctx->d_flag);
+    weights_serial_kernel<<<1, 1, 0, s>>>(key, count, d_out, ctx->d_flag, (int)(flags & 1u));
+    ctx->launches += 2; CK(cudaGetLastError());
+    return OMR_OK;
+}
+int decrypt_decode_impl(omr_ctx* ctx, const u64* d_z2_ntt, const u64* d_ct, size_t n, unsigned short* d_out, cudaStream_t s) {
+    if (!n) return OMR_OK;
+    int st; if ((st = ensure_partial(ctx, n * F2::N))) return st;
+    const size_t total = n * F2::N;
+    decrypt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_ct, d_z2_ntt, ctx->s_partial, n);
+    ++ctx->launches; CK(cudaGetLastError());
+    ntt_kernel<F2, true><<<(unsigned)n, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ctx->s_partial, ctx->tb, ctx->n2_inv);
+    ++ctx->launches; CK(cudaGetLastError());
+    decode_round_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ctx->s_partial, d_out, total);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+// n_polys second-level polynomials in place: NTT-native -> coefficient form (scaled by N^-1) or back
+int to_coeff_impl(omr_ctx* ctx, u64* d_polys, size_t n_polys, cudaStream_t s) {
+    if (!n_polys) return OMR_OK;
+    ntt_kernel<F2, true><<<(unsigned)n_polys, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(d_polys, ctx->tb, ctx->n2_inv);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+int from_coeff_impl(omr_ctx* ctx, u64* d_polys, size_t n_polys, cudaStream_t s) {
+    if (!n_polys) return OMR_OK;
+    ntt_kernel<F2, false><<<(unsigned)n_polys, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(d_polys, ctx->tb, ctx->n2_inv);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+// device -> host copy of n ciphertexts in the context's output domain (OMR_OUT_COEFF: through a bounded staging buffer so
+// that the resident NTT-native data stays untouched)
+int copy_out_cts(omr_ctx* ctx, uint64_t* h_out, const u64* d_src, size_t n, cudaStream_t s) {
+    if (!n) return OMR_OK;
+    if (ctx->out_domain == OMR_OUT_NTT_NATIVE) {
+        CK(cudaMemcpyAsync(h_out, d_src, n * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        return OMR_OK;
+    }
+    const size_t STAGE = 1024;                                   // 32 MiB
+    if (ctx->coeff_words < STAGE * OMR_PV_WORDS) {
+        cudaFree(ctx->s_coeff); ctx->s_coeff = nullptr; ctx->coeff_words = 0;
+        int st; if ((st = dalloc(ctx, &ctx->s_coeff, STAGE * OMR_PV_WORDS))) return st;
+        ctx->coeff_words = STAGE * OMR_PV_WORDS;
+    }
+    for (size_t off = 0; off < n; off += STAGE) {
+        const size_t nb = n - off < STAGE ? n - off : STAGE;
+        CK(cudaMemcpyAsync(ctx->s_coeff, d_src + off * OMR_PV_WORDS, nb * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        int st; if ((st = to_coeff_impl(ctx, ctx->s_coeff, 2 * nb, s))) return st;
+        CK(cudaMemcpyAsync(h_out + off * OMR_PV_WORDS, ctx->s_coeff, nb * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    }
+    return OMR_OK;
+}
+int ensure_elems(omr_ctx* ctx, unsigned short** p, size_t* have, size_t need) {
+    if (need <= *have) return OMR_OK;
+    cudaFree(*p); *p = nullptr; *have = 0;
+    int st; if ((st = dalloc(ctx, p, need))) return st;
+    *have = need;
+    return OMR_OK;
+}
+int ensure_clues(omr_ctx* ctx, size_t B) {
+    if (B <= ctx->clue_cap) return OMR_OK;
+    cudaFree(ctx->s_ca); cudaFree(ctx->s_cb); ctx->s_ca = nullptr; ctx->s_cb = nullptr; ctx->clue_cap = 0;
+    int st;
+    if ((st = dalloc(ctx, &ctx->s_ca, B * CLUE_N))) return st;
+    if ((st = dalloc(ctx, &ctx->s_cb, B * CLUE_COUNT))) return st;
+    ctx->clue_cap = B;
+    return OMR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- device-pointer forms ----------------------------------------------------------------------------------------------
+int omr_detect_batch_device(omr_ctx* ctx, const uint16_t* d_clue_a, const uint16_t* d_clue_b, size_t B, uint64_t* d_pv, void* stream,
+                            omr_stage_times* times) {
+    if (!ctx || (B && (!d_clue_a || !d_clue_b || !d_pv))) { ctx_fail(ctx, "detect: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
+    return detect_device(ctx, d_clue_a, d_clue_b, B, (u64*)d_pv, (cudaStream_t)stream, times);
+}
+int omr_l1_blind_rotate_device(omr_ctx* ctx, const uint16_t* a, const uint16_t* b, size_t B, uint32_t* d_rlwe, void* stream) {
+    if (!ctx) return OMR_ERR_INVALID;
+    ENTER(ctx);
+    return launch_l1(ctx, a, b, B, d_rlwe, (cudaStream_t)stream);
+}
+int omr_keyswitch_device(omr_ctx* ctx, const uint32_t* d_rlwe, size_t B, uint32_t* d_lwe, void* stream) {
+    if (!ctx) return OMR_ERR_INVALID;
+    ENTER(ctx);
+    return launch_ks(ctx, d_rlwe, B, d_lwe, (cudaStream_t)stream);
+}
+int omr_l2_blind_rotate_device(omr_ctx* ctx, const uint32_t* d_lwe, size_t B, uint64_t* d_rlwe, void* stream) {
+    if (!ctx) return OMR_ERR_INVALID;
+    ENTER(ctx);
+    return launch_l2(ctx, d_lwe, B, (u64*)d_rlwe, (cudaStream_t)stream);
+}
+int omr_trace_device(omr_ctx* ctx, uint64_t* d_rlwe, size_t B, void* stream) {
+    if (!ctx) return OMR_ERR_INVALID;
+    ENTER(ctx);
+    return launch_trace(ctx, (u64*)d_rlwe, B, (cudaStream_t)stream);
+}
+int omr_ntt_forward_device(omr_ctx* ctx, int level, void* d, size_t batch, void* stream) {
+    if (!ctx || (level != 1 && level != 2)) return OMR_ERR_INVALID;
+    ENTER(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!batch) return OMR_OK;
+    if (level == 1) ntt_kernel<F1, false><<<(unsigned)batch, ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>((u32*)d, ctx->tb, ctx->n1_inv);
+    else ntt_kernel<F2, false><<<(unsigned)batch, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>((u64*)d, ctx->tb, ctx->n2_inv);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+int omr_ntt_inverse_device(omr_ctx* ctx, int level, void* d, size_t batch, void* stream) {
+    if (!ctx || (level != 1 && level != 2)) return OMR_ERR_INVALID;
+    ENTER(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!batch) return OMR_OK;
+    if (level == 1) ntt_kernel<F1, true><<<(unsigned)batch, ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>((u32*)d, ctx->tb, ctx->n1_inv);
+    else ntt_kernel<F2, true><<<(unsigned)batch, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>((u64*)d, ctx->tb, ctx->n2_inv);
+    ++ctx->launches; CK(cudaGetLastError());
+    return OMR_OK;
+}
+
 int omr_encode_indices_device(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* d_pv, size_t count, uint64_t index0,
                               uint64_t seed, uint32_t cipher_idx0, uint32_t n_cipher, uint64_t* d_out, void* stream) {
     if (!ctx || !d_out || (count && !d_pv)) { ctx_fail(ctx, "encode_indices: null argument"); return OMR_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    int st; if ((st = check_rp(ctx, rp))) return st;
-    PackIndexArgs ia{rp->slots_per_bucket, rp->slots_per_segment, rp->segment_per_cipher, rp->bucket_count_per_segment, seed, cipher_idx0};
-    return pack_device(ctx, true, (const u64*)d_pv, count, index0, ia, PackPayloadArgs{}, n_cipher, (u64*)d_out,
-                       (cudaStream_t)stream);
+    ENTER(ctx);
+    return encode_indices_impl(ctx, rp, (const u64*)d_pv, count, index0, seed, cipher_idx0, n_cipher, (u64*)d_out, (cudaStream_t)stream);
 }
 int omr_encode_payloads_device(omr_ctx* ctx, const uint64_t* d_pv, const uint16_t* d_payloads, size_t count, uint64_t index0,
                                const uint16_t* d_weights, size_t weight_stride, uint32_t n_cipher, uint32_t cmb_per_cipher, uint64_t* d_out,
                                void* stream) {
     if (!ctx || !d_out || (count && (!d_pv || !d_payloads || !d_weights))) { ctx_fail(ctx, "encode_payloads: null argument"); return OMR_ERR_INVALID; }
-    if (cmb_per_cipher == 0 || cmb_per_cipher * OMR_PAYLOAD_LEN > OMR_N2 || index0 + count > weight_stride) {
-        ctx_fail(ctx, "encode_payloads: bad combination layout"); return OMR_ERR_INVALID;
-    }
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    PackPayloadArgs pa{d_payloads, d_weights, weight_stride, cmb_per_cipher};
-    return pack_device(ctx, false, (const u64*)d_pv, count, index0, PackIndexArgs{}, pa, n_cipher, (u64*)d_out,
-                       (cudaStream_t)stream);
+    ENTER(ctx);
+    return encode_payloads_impl(ctx, (const u64*)d_pv, d_payloads, count, index0, d_weights, weight_stride, n_cipher, cmb_per_cipher, (u64*)d_out,
+                                (cudaStream_t)stream);
 }
 int omr_digest_reduce_mod(omr_ctx* ctx, uint64_t* d_words, size_t n, void* stream) {
     if (!ctx || (n && !d_words)) return OMR_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     if (!n) return OMR_OK;
     digest_mod_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((u64*)d_words, n);
     ++ctx->launches; CK(cudaGetLastError());
@@ -591,7 +724,7 @@ int omr_digest_reduce_mod(omr_ctx* ctx, uint64_t* d_words, size_t n, void* strea
 
 int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, size_t n, void* stream) {
     if (!ctx || (n && (!d_acc || !d_part))) return OMR_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     if (!n) return OMR_OK;
     digest_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((u64*)d_acc, (const u64*)d_part, n);
     ++ctx->launches; CK(cudaGetLastError());
@@ -600,42 +733,22 @@ int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, si
 
 int omr_decrypt_decode_device(omr_ctx* ctx, const uint64_t* d_z2_ntt, const uint64_t* d_ct, size_t n, uint16_t* d_out, void* stream) {
     if (!ctx || (n && (!d_z2_ntt || !d_ct || !d_out))) { ctx_fail(ctx, "decrypt_decode: null argument"); return OMR_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    if (!n) return OMR_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    int st; if ((st = ensure_partial(ctx, n * F2::N))) return st;
-    const size_t total = n * F2::N;
-    decrypt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const u64*)d_ct, (const u64*)d_z2_ntt, ctx->s_partial, n);
-    ++ctx->launches; CK(cudaGetLastError());
-    ntt_kernel<F2, true><<<(unsigned)n, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ctx->s_partial, ctx->tb, ctx->n2_inv);
-    ++ctx->launches; CK(cudaGetLastError());
-    decode_round_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ctx->s_partial, d_out, total);
-    ++ctx->launches; CK(cudaGetLastError());
-    return OMR_OK;
+    ENTER(ctx);
+    return decrypt_decode_impl(ctx, (const u64*)d_z2_ntt, (const u64*)d_ct, n, d_out, (cudaStream_t)stream);
 }
 
 int omr_weights_from_seed_device(omr_ctx* ctx, const uint8_t* seed32, size_t count, uint16_t* d_out, uint32_t flags, void* stream) {
     if (!ctx || (count && (!seed32 || !d_out))) { ctx_fail(ctx, "weights_from_seed: null argument"); return OMR_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-    if (!count) return OMR_OK;
-    if (!ctx->d_flag) CK(cudaMalloc((void**)&ctx->d_flag, sizeof(int)));
-    ChaChaKey key;
-    for (int i = 0; i < 8; ++i) key.k[i] = (u32)seed32[4 * i] | ((u32)seed32[4 * i + 1] << 8) | ((u32)seed32[4 * i + 2] << 16) | ((u32)seed32[4 * i + 3] << 24);
-    cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s));
-    const size_t blocks = (count + 15) / 16;
-    weights_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, s>>>(key, count, d_out, ctx->d_flag);
-    weights_serial_kernel<<<1, 1, 0, s>>>(key, count, d_out, ctx->d_flag, (int)(flags & 1u));
-    ctx->launches += 2; CK(cudaGetLastError());
-    return OMR_OK;
+    ENTER(ctx);
+    return weights_from_seed_impl(ctx, seed32, count, d_out, flags, (cudaStream_t)stream);
 }
 
-int omr_gen_clues_device(omr_ctx* ctx, const uint16_t* d_pa, const uint16_t* d_pb, uint64_t seed, uint64_t index0, size_t count,
+int omr_gen_clues_device(omr_ctx* ctx, const uint16_t* d_pa, const uint16_t* d_pb, const uint8_t* seed32, uint64_t index0, size_t count,
                          const uint8_t* d_msgs, uint16_t* d_a, uint16_t* d_b, void* stream) {
-    if (!ctx || (count && (!d_pa || !d_pb || !d_a || !d_b))) { ctx_fail(ctx, "gen_clues: null argument"); return OMR_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
+    if (!ctx || !seed32 || (count && (!d_pa || !d_pb || !d_a || !d_b))) { ctx_fail(ctx, "gen_clues: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
     if (!count) return OMR_OK;
-    clue_gen_kernel<<<(unsigned)count, CLUE_THREADS, 0, (cudaStream_t)stream>>>(d_pa, d_pb, seed, index0, d_msgs, d_a, d_b);
+    clue_gen_kernel<<<(unsigned)count, CLUE_THREADS, 0, (cudaStream_t)stream>>>(d_pa, d_pb, chacha_key_from_seed(seed32), index0, d_msgs, d_a, d_b);
     ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
@@ -651,8 +764,7 @@ int omr_pv_reset(omr_ctx* ctx) {
 int omr_detect_batch(omr_ctx* ctx, const uint16_t* clue_a, const uint16_t* clue_b, size_t B, uint64_t global_index0, uint64_t* pv_out,
                      omr_stage_times* times) {
     if (!ctx || (B && (!clue_a || !clue_b))) { ctx_fail(ctx, "detect: null argument"); return OMR_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx);
     if (times) *times = omr_stage_times{};
     if (!B) return OMR_OK;
     // the store holds one contiguous run of global indices
@@ -660,60 +772,55 @@ int omr_detect_batch(omr_ctx* ctx, const uint16_t* clue_a, const uint16_t* clue_
     if (global_index0 != ctx->pv_index0 + ctx->pv_count) { ctx_fail(ctx, "detect: global_index0 must continue the pertinency store"); return OMR_ERR_STATE; }
     int st;
     if ((st = ensure_pv(ctx, ctx->pv_count + B))) return st;
-    const size_t MAXB = 16384;
-    if ((st = ensure_scratch(ctx, B < MAXB ? B : MAXB))) return st;
+    if ((st = ensure_clues(ctx, B))) return st;
     cudaStream_t s = ctx->stream;
-    for (size_t off = 0; off < B; off += MAXB) {
-        const size_t nb = B - off < MAXB ? B - off : MAXB;
-        CK(cudaMemcpyAsync(ctx->s_ca, clue_a + off * CLUE_N, nb * CLUE_N * 2, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->s_cb, clue_b + off * CLUE_COUNT, nb * CLUE_COUNT * 2, cudaMemcpyHostToDevice, s));
-        u64* dst = ctx->pv + (ctx->pv_count + off) * OMR_PV_WORDS;
-        omr_stage_times tt;
-        if ((st = detect_device(ctx, ctx->s_ca, ctx->s_cb, nb, dst, s, times ? &tt : nullptr))) return st;
-        if (times) {
-            times->detect_ms += tt.detect_ms; times->first_level_bootstrapping_ms += tt.first_level_bootstrapping_ms;
-            times->second_level_bootstrapping_ms += tt.second_level_bootstrapping_ms; times->trace_ms += tt.trace_ms;
-        }
-        if (pv_out) CK(cudaMemcpyAsync(pv_out + off * OMR_PV_WORDS, dst, nb * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));       // scratch clue buffers are reused by the next chunk
-    }
+    // all clues of the call are staged at once (1 038 bytes per message), so the chunks of detect_device run back to back
+    // with no host synchronisation in between
+    CK(cudaMemcpyAsync(ctx->s_ca, clue_a, B * CLUE_N * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->s_cb, clue_b, B * CLUE_COUNT * 2, cudaMemcpyHostToDevice, s));
+    u64* dst = ctx->pv + ctx->pv_count * OMR_PV_WORDS;
+    if ((st = detect_device(ctx, ctx->s_ca, ctx->s_cb, B, dst, s, times))) return st;
+    if (pv_out && (st = copy_out_cts(ctx, pv_out, dst, B, s))) return st;
+    CK(cudaStreamSynchronize(s));
     ctx->pv_count += B; ctx->pv_any = true;
     return OMR_OK;
 }
 
 int omr_encode_indices(omr_ctx* ctx, const omr_retrieval_params* rp, uint64_t seed, uint32_t cipher_idx0, uint32_t n_cipher, uint64_t* out) {
     if (!ctx || !out) { ctx_fail(ctx, "encode_indices: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);                                       // held across the launches AND the copy out of the shared digest buffer
+    if (!ctx->pv_any) { ctx_fail(ctx, "encode_indices: empty pertinency store"); return OMR_ERR_STATE; }
     int st;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-        if (!ctx->pv_any) { ctx_fail(ctx, "encode_indices: empty pertinency store"); return OMR_ERR_STATE; }
-        if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
-    }
-    if ((st = omr_encode_indices_device(ctx, rp, ctx->pv, ctx->pv_count, ctx->pv_index0, seed, cipher_idx0, n_cipher, ctx->s_digest, ctx->stream))) return st;
-    CK(cudaMemcpyAsync(out, ctx->s_digest, (size_t)n_cipher * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
+    if ((st = encode_indices_impl(ctx, rp, ctx->pv, ctx->pv_count, ctx->pv_index0, seed, cipher_idx0, n_cipher, ctx->s_digest, ctx->stream))) return st;
+    if ((st = copy_out_cts(ctx, out, ctx->s_digest, n_cipher, ctx->stream))) return st;
     CK(cudaStreamSynchronize(ctx->stream));
     return OMR_OK;
 }
 
-int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, const uint16_t* weights, size_t weight_stride, uint32_t n_cipher,
-                        uint32_t cmb_per_cipher, uint64_t* out) {
+int omr_encode_payloads(omr_ctx* ctx, const uint16_t* payloads, size_t count, const uint16_t* weights, size_t weight_rows, size_t weight_stride,
+                        uint32_t n_cipher, uint32_t cmb_per_cipher, uint64_t* out) {
     if (!ctx || !out || !payloads || !weights) { ctx_fail(ctx, "encode_payloads: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
+    if (!ctx->pv_any) { ctx_fail(ctx, "encode_payloads: empty pertinency store"); return OMR_ERR_STATE; }
+    if (count != ctx->pv_count) { ctx_fail(ctx, "encode_payloads: payload count != pertinency store size"); return OMR_ERR_INVALID; }
+    const size_t rows = (size_t)n_cipher * cmb_per_cipher;
+    // the reference allocates ceil(cc / per) * per rows and fills the first combination_count (detector.rs:370-387): the caller
+    // passes the rows it has, the missing tail rows are zero
+    if (weight_rows == 0 || weight_rows > rows) { ctx_fail(ctx, "encode_payloads: weight_rows must be in [1, n_cipher * cmb_per_cipher]"); return OMR_ERR_INVALID; }
     int st;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-        if (!ctx->pv_any) { ctx_fail(ctx, "encode_payloads: empty pertinency store"); return OMR_ERR_STATE; }
-        if (count != ctx->pv_count) { ctx_fail(ctx, "encode_payloads: payload count != pertinency store size"); return OMR_ERR_INVALID; }
-        if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
-        const size_t pe = count * OMR_PAYLOAD_LEN, we = (size_t)n_cipher * cmb_per_cipher * weight_stride;
-        if (pe > ctx->payload_elems) { cudaFree(ctx->s_payloads); ctx->s_payloads = nullptr; ctx->payload_elems = 0; if ((st = dalloc(ctx, &ctx->s_payloads, pe))) return st; ctx->payload_elems = pe; }
-        if (we > ctx->weight_elems) { cudaFree(ctx->s_weights); ctx->s_weights = nullptr; ctx->weight_elems = 0; if ((st = dalloc(ctx, &ctx->s_weights, we))) return st; ctx->weight_elems = we; }
-        CK(cudaMemcpyAsync(ctx->s_payloads, payloads, pe * 2, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->s_weights, weights, we * 2, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if ((st = omr_encode_payloads_device(ctx, ctx->pv, ctx->s_payloads, count, ctx->pv_index0, ctx->s_weights, weight_stride, n_cipher, cmb_per_cipher,
-                                         ctx->s_digest, ctx->stream))) return st;
-    CK(cudaMemcpyAsync(out, ctx->s_digest, (size_t)n_cipher * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
+    const size_t pe = count * OMR_PAYLOAD_LEN, we = rows * weight_stride;
+    if ((st = ensure_elems(ctx, &ctx->s_payloads, &ctx->payload_elems, pe))) return st;
+    if ((st = ensure_elems(ctx, &ctx->s_weights, &ctx->weight_elems, we))) return st;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->s_payloads, payloads, pe * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->s_weights, weights, weight_rows * weight_stride * 2, cudaMemcpyHostToDevice, s));
+    if (weight_rows < rows) CK(cudaMemsetAsync(ctx->s_weights + weight_rows * weight_stride, 0, (rows - weight_rows) * weight_stride * 2, s));
+    if ((st = encode_payloads_impl(ctx, ctx->pv, ctx->s_payloads, count, ctx->pv_index0, ctx->s_weights, weight_stride, n_cipher, cmb_per_cipher,
+                                   ctx->s_digest, s))) return st;
+    if ((st = copy_out_cts(ctx, out, ctx->s_digest, n_cipher, s))) return st;
+    CK(cudaStreamSynchronize(s));
     return OMR_OK;
 }
 
@@ -723,27 +830,27 @@ int omr_encode_payloads_seeded(omr_ctx* ctx, const uint16_t* payloads, size_t co
     if (!ctx || !out || !payloads || !seed32 || !cmb_per_cipher || !combination_count) { ctx_fail(ctx, "encode_payloads_seeded: bad argument"); return OMR_ERR_INVALID; }
     const uint32_t n_cipher = (combination_count + cmb_per_cipher - 1) / cmb_per_cipher;
     const size_t rows = (size_t)n_cipher * cmb_per_cipher, we = rows * all_payloads_count, pe = count * OMR_PAYLOAD_LEN;
+    ENTER(ctx);
+    if (!ctx->pv_any) { ctx_fail(ctx, "encode_payloads: empty pertinency store"); return OMR_ERR_STATE; }
+    if (count != ctx->pv_count) { ctx_fail(ctx, "encode_payloads: payload count != pertinency store size"); return OMR_ERR_INVALID; }
+    if (ctx->pv_index0 + count > all_payloads_count) { ctx_fail(ctx, "encode_payloads: store exceeds all_payloads_count"); return OMR_ERR_INVALID; }
     int st;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu); CK(cudaSetDevice(ctx->device));
-        if (!ctx->pv_any) { ctx_fail(ctx, "encode_payloads: empty pertinency store"); return OMR_ERR_STATE; }
-        if (count != ctx->pv_count) { ctx_fail(ctx, "encode_payloads: payload count != pertinency store size"); return OMR_ERR_INVALID; }
-        if (ctx->pv_index0 + count > all_payloads_count) { ctx_fail(ctx, "encode_payloads: store exceeds all_payloads_count"); return OMR_ERR_INVALID; }
-        if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
-        if (pe > ctx->payload_elems) { cudaFree(ctx->s_payloads); ctx->s_payloads = nullptr; ctx->payload_elems = 0; if ((st = dalloc(ctx, &ctx->s_payloads, pe))) return st; ctx->payload_elems = pe; }
-        if (we > ctx->weight_elems) { cudaFree(ctx->s_weights); ctx->s_weights = nullptr; ctx->weight_elems = 0; if ((st = dalloc(ctx, &ctx->s_weights, we))) return st; ctx->weight_elems = we; }
-        CK(cudaMemcpyAsync(ctx->s_payloads, payloads, pe * 2, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(ctx->s_weights, 0, we * 2, ctx->stream));            // unused tail rows stay zero (detector.rs:370-371)
-    }
-    if ((st = omr_weights_from_seed_device(ctx, seed32, (size_t)combination_count * all_payloads_count, ctx->s_weights, 0, ctx->stream))) return st;
-    if ((st = omr_encode_payloads_device(ctx, ctx->pv, ctx->s_payloads, count, ctx->pv_index0, ctx->s_weights, all_payloads_count, n_cipher, cmb_per_cipher,
-                                         ctx->s_digest, ctx->stream))) return st;
-    CK(cudaMemcpyAsync(out, ctx->s_digest, (size_t)n_cipher * OMR_PV_WORDS * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if ((st = ensure_digest(ctx, (size_t)n_cipher * OMR_PV_WORDS))) return st;
+    if ((st = ensure_elems(ctx, &ctx->s_payloads, &ctx->payload_elems, pe))) return st;
+    if ((st = ensure_elems(ctx, &ctx->s_weights, &ctx->weight_elems, we))) return st;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->s_payloads, payloads, pe * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->s_weights, 0, we * 2, s));                      // unused tail rows stay zero (detector.rs:370-371)
+    if ((st = weights_from_seed_impl(ctx, seed32, (size_t)combination_count * all_payloads_count, ctx->s_weights, 0, s))) return st;
+    if ((st = encode_payloads_impl(ctx, ctx->pv, ctx->s_payloads, count, ctx->pv_index0, ctx->s_weights, all_payloads_count, n_cipher, cmb_per_cipher,
+                                   ctx->s_digest, s))) return st;
+    if ((st = copy_out_cts(ctx, out, ctx->s_digest, n_cipher, s))) return st;
+    CK(cudaStreamSynchronize(s));
     return OMR_OK;
 }
 
 // ---- recipient side, host-buffer form (Retriever::decode_digest, retriever.rs:188-260) -------------------------------------
+}  // extern "C"
 namespace {
 // solve_matrix_mod_257 (matrix.rs:164-247): Gaussian elimination over Z_257 on (m [rows][cols], pl [rows][612]); first
 // non-zero pivot, row swap, normalise, eliminate below, back-substitute.  false = singular (OmrError::InvertibleMatrix).
@@ -783,11 +890,12 @@ bool solve_mod_257(std::vector<u32>& m, std::vector<u32>& pl, size_t rows, size_
     return true;
 }
 }  // namespace
+extern "C" {
 
-int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* z2_ntt, const uint64_t* index_cts, uint32_t n_index_cts,
+int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64_t* z2, const uint64_t* index_cts, uint32_t n_index_cts,
                       const uint64_t* payload_cts, uint32_t n_payload_cts, const uint16_t* weights, size_t weight_stride,
                       uint64_t* indices_out, uint32_t* n_found, uint16_t* payloads_out) {
-    if (!ctx || !rp || !z2_ntt || !index_cts || !payload_cts || !weights || !indices_out || !n_found || !payloads_out) {
+    if (!ctx || !rp || !z2 || !index_cts || !payload_cts || !weights || !indices_out || !n_found || !payloads_out) {
         ctx_fail(ctx, "decode_digest: null argument"); return OMR_ERR_INVALID;
     }
     *n_found = 0;
@@ -799,22 +907,28 @@ int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64
     const size_t n = (size_t)n_index_cts + n_payload_cts;
     std::vector<uint16_t> slots(n * OMR_N2);
     {   // decrypt + inverse NTT + exact-integer decode of every slot on the GPU
+        ENTER(ctx);
         u64 *d_key = nullptr, *d_ct = nullptr; uint16_t* d_out = nullptr;
         auto release = [&]() { cudaFree(d_key); cudaFree(d_ct); cudaFree(d_out); };
-        cudaError_t e = cudaSetDevice(ctx->device);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_key, OMR_N2 * sizeof(u64));
+        cudaStream_t s = ctx->stream;
+        cudaError_t e = cudaMalloc((void**)&d_key, OMR_N2 * sizeof(u64));
         if (e == cudaSuccess) e = cudaMalloc((void**)&d_ct, n * OMR_PV_WORDS * sizeof(u64));
         if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, n * OMR_N2 * sizeof(uint16_t));
-        if (e == cudaSuccess) e = cudaMemcpy(d_key, z2_ntt, OMR_N2 * sizeof(u64), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_ct, index_cts, (size_t)n_index_cts * OMR_PV_WORDS * sizeof(u64), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_ct + (size_t)n_index_cts * OMR_PV_WORDS, payload_cts, (size_t)n_payload_cts * OMR_PV_WORDS * sizeof(u64), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_key, z2, OMR_N2 * sizeof(u64), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ct, index_cts, (size_t)n_index_cts * OMR_PV_WORDS * sizeof(u64), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_ct + (size_t)n_index_cts * OMR_PV_WORDS, payload_cts, (size_t)n_payload_cts * OMR_PV_WORDS * sizeof(u64), cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { release(); ctx_fail(ctx, std::string("decode_digest: ") + cudaGetErrorString(e)); return OMR_ERR_CUDA; }
-        int st = omr_decrypt_decode_device(ctx, d_key, d_ct, n, d_out, ctx->stream);
-        if (st == OMR_OK) {
-            e = cudaMemcpyAsync(slots.data(), d_out, slots.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) { ctx_fail(ctx, std::string("decode_digest: ") + cudaGetErrorString(e)); st = OMR_ERR_CUDA; }
+        int st = OMR_OK;
+        if (ctx->out_domain == OMR_OUT_COEFF) {                      // coefficient-form secret and ciphertexts: transform on the way in
+            st = from_coeff_impl(ctx, d_key, 1, s);
+            if (st == OMR_OK) st = from_coeff_impl(ctx, d_ct, 2 * n, s);
         }
+        if (st == OMR_OK) st = decrypt_decode_impl(ctx, d_key, d_ct, n, d_out, s);
+        if (st == OMR_OK) {
+            e = cudaMemcpyAsync(slots.data(), d_out, slots.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { ctx_fail(ctx, std::string("decode_digest: ") + cudaGetErrorString(e)); st = OMR_ERR_CUDA; }
+        } else cudaStreamSynchronize(s);
         release();
         if (st) return st;
     }

@@ -6,7 +6,8 @@
 //   K5 pack_kernel<INDICES>      detector.rs:223-339            index digest
 //   K6 pack_kernel<PAYLOADS>     detector.rs:341-453            payload digest
 // plus partial-sum reduction, batched standalone NTTs and the key pre-transforms.
-// Tensor cores are deliberately unused: the contraction here is an exact modular NTT, not a floating-point GEMM.
+// Everything here runs on the CUDA cores (integer and FP64 pipes): the contraction is an exact modular NTT, not a floating-point
+// GEMM.  The one GEMM-shaped stage, the LWE key switch, has an opt-in tensor-core variant (ks_gemm.cu).
 #pragma once
 #include "ntt.cuh"
 
@@ -929,59 +930,19 @@ __global__ void decode_round_kernel(const u64* __restrict__ in /*[n][N] canonica
     out[i] = (unsigned short)t;
 }
 
-// ---- sender side (SURVEY §8f.2): batched clue generation -------------------------------------------------------------------
-// ClueKey::gen_clues (key_gen/clue.rs:27-34 -> [UPSTREAM] LwePublicKeyRlweMode::encrypt_multi_messages, SURVEY A.3): with the
-// public key (pa, pb = pa*s0 + e) over Z_2048[X]/(X^512+1): clue = (pa*r + e1, first 7 coefficients of pb*r + e2 + 256*m),
-// r binary.  One CTA per clue; every random draw is a counter hash of (seed, message index, domain, position) and the
-// rounded Gaussian comes from an integer cumulative table — bit-identical to the oracle's gen_clue_cb.
-__constant__ u32 CLUE_CDT[5] = {1947496405u, 3992218608u, 4283915214u, 4294862567u, 4294967049u};   // P(|e| <= k) 2^32, sigma 0.8293
-__device__ __forceinline__ u64 clue_hash(u64 seed, u64 index, u32 domain, u32 pos) {
-    return mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (index + 1)) ^ ((((u64)domain << 32) | pos) * 0xD1342543DE82EF95ull));
-}
-__device__ __forceinline__ int clue_gauss(u64 h) {
-    const u32 u = (u32)h; int m = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) m += u >= CLUE_CDT[k];
-    return (h >> 63) ? -m : m;
-}
-constexpr int CLUE_THREADS = 256;
-__global__ void __launch_bounds__(CLUE_THREADS)
-clue_gen_kernel(const unsigned short* __restrict__ pa, const unsigned short* __restrict__ pb, u64 seed, u64 index0,
-                const unsigned char* __restrict__ msgs /*nullable [count][7]*/, unsigned short* __restrict__ out_a, unsigned short* __restrict__ out_b) {
-    __shared__ unsigned short s_pa[CLUE_N], s_pb[CLUE_N];
-    __shared__ unsigned char s_r[CLUE_N];
-    const u64 index = index0 + blockIdx.x;
-    for (int j = threadIdx.x; j < CLUE_N; j += CLUE_THREADS) {
-        s_pa[j] = pa[j]; s_pb[j] = pb[j];
-        s_r[j] = (unsigned char)(clue_hash(seed, index, 0, (u32)j) & 1);
-    }
-    __syncthreads();
-    // (p * r)[i] = SUM_{j<=i} p[i-j] r[j] - SUM_{j>i} p[512+i-j] r[j]   (negacyclic, mod 2048 by wrap-around of int32)
-    for (int i = threadIdx.x; i < CLUE_N; i += CLUE_THREADS) {
-        int acc = 0;
-        for (int j = 0; j <= i; ++j) acc += s_r[j] ? (int)s_pa[i - j] : 0;
-        for (int j = i + 1; j < CLUE_N; ++j) acc -= s_r[j] ? (int)s_pa[CLUE_N + i - j] : 0;
-        out_a[(size_t)blockIdx.x * CLUE_N + i] = (unsigned short)((acc + clue_gauss(clue_hash(seed, index, 1, (u32)i))) & (CLUE_Q - 1));
-    }
-    if (threadIdx.x < CLUE_COUNT) {
-        const int c = threadIdx.x;
-        int acc = 0;
-        for (int j = 0; j <= c; ++j) acc += s_r[j] ? (int)s_pb[c - j] : 0;
-        for (int j = c + 1; j < CLUE_N; ++j) acc -= s_r[j] ? (int)s_pb[CLUE_N + c - j] : 0;
-        const int m = msgs ? (int)(msgs[(size_t)blockIdx.x * CLUE_COUNT + c] & 7) * (CLUE_Q / 8) : 0;
-        out_b[(size_t)blockIdx.x * CLUE_COUNT + c] = (unsigned short)((acc + clue_gauss(clue_hash(seed, index, 2, (u32)c)) + m) & (CLUE_Q - 1));
-    }
-}
-
-// ---- combination weights from the reference's 32-byte seed ------------------------------------------------------------------
-// detector.rs:376-387 / retriever.rs:215-226: StdRng::from_seed(seed) (rand 0.8: ChaCha12, 64-bit block counter from 0, stream
-// 0) drives Uniform::<u16>::new(0, 257).sample_iter: one u32 per draw, v * 257 = hi:lo, accept when lo <= zone (zone = 2^32 - 2:
-// one u32 value in 2^32 is rejected), weight = hi.  One thread per 64-byte ChaCha block = 16 draws.  A rejection shifts every
-// later draw, so the parallel kernel only flags it and weights_serial_kernel then regenerates the whole stream in order.
+// ---- ChaCha12 (the core of rand 0.8's StdRng) -------------------------------------------------------------------------------
+// Used for (i) the combination weights exactly as the reference draws them (below) and (ii) every random draw of the sender
+// side, which the reference requires to come from a CryptoRng (key_gen/clue.rs:27-30, sender.rs:27-30).
 struct ChaChaKey { u32 k[8]; };
-__device__ __forceinline__ void chacha12_block(const ChaChaKey& key, u64 counter, u32 (&out)[16]) {
+inline ChaChaKey chacha_key_from_seed(const uint8_t* seed32) {
+    ChaChaKey key;
+    for (int i = 0; i < 8; ++i) key.k[i] = (u32)seed32[4 * i] | ((u32)seed32[4 * i + 1] << 8) | ((u32)seed32[4 * i + 2] << 16) | ((u32)seed32[4 * i + 3] << 24);
+    return key;
+}
+// state words 12,13 = 64-bit counter, 14,15 = nonce (n0, n1); StdRng is counter = block index from 0, nonce = 0
+__device__ __forceinline__ void chacha12_block(const ChaChaKey& key, u64 counter, u32 n0, u32 n1, u32 (&out)[16]) {
     const u32 st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.k[0], key.k[1], key.k[2], key.k[3],
-                        key.k[4], key.k[5], key.k[6], key.k[7], (u32)counter, (u32)(counter >> 32), 0u, 0u};
+                        key.k[4], key.k[5], key.k[6], key.k[7], (u32)counter, (u32)(counter >> 32), n0, n1};
     u32 x[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = st[i];
@@ -997,13 +958,70 @@ __device__ __forceinline__ void chacha12_block(const ChaChaKey& key, u64 counter
 #pragma unroll
     for (int i = 0; i < 16; ++i) out[i] = x[i] + st[i];
 }
+
+// ---- sender side (SURVEY §8f.2): batched clue generation -------------------------------------------------------------------
+// ClueKey::gen_clues (key_gen/clue.rs:27-34 -> [UPSTREAM] LwePublicKeyRlweMode::encrypt_multi_messages, SURVEY A.3): with the
+// public key (pa, pb = pa*s0 + e) over Z_2048[X]/(X^512+1): clue = (pa*r + e1, first 7 coefficients of pb*r + e2 + 256*m),
+// r binary.  One CTA per clue.  Randomness: ChaCha12 keyed by the caller's 32-byte seed in counter mode — block
+// (counter = global message index, nonce = (domain, block)) with domain 1 = the 512 bits of r (one block), domain 2 = the 512
+// errors e1 (64 bits per draw, 8 draws per block), domain 3 = the 7 errors e2 — so clues are independent of batching and GPU
+// count and the mask r is unpredictable without the seed.  The rounded Gaussian comes from an integer cumulative table.
+// Bit-identical to the oracle's gen_clue_cb.
+__constant__ u32 CLUE_CDT[5] = {1947496405u, 3992218608u, 4283915214u, 4294862567u, 4294967049u};   // P(|e| <= k) 2^32, sigma 0.8293
+__device__ __forceinline__ int clue_gauss(u64 h) {
+    const u32 u = (u32)h; int m = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) m += u >= CLUE_CDT[k];
+    return (h >> 63) ? -m : m;
+}
+constexpr int CLUE_THREADS = 256;
+__global__ void __launch_bounds__(CLUE_THREADS)
+clue_gen_kernel(const unsigned short* __restrict__ pa, const unsigned short* __restrict__ pb, ChaChaKey key, u64 index0,
+                const unsigned char* __restrict__ msgs /*nullable [count][7]*/, unsigned short* __restrict__ out_a, unsigned short* __restrict__ out_b) {
+    __shared__ unsigned short s_pa[CLUE_N], s_pb[CLUE_N];
+    __shared__ unsigned char s_r[CLUE_N];
+    __shared__ u32 s_rw[16], s_e2[16];
+    const u64 index = index0 + blockIdx.x;
+    if (threadIdx.x == 0) { u32 w[16]; chacha12_block(key, index, 1u, 0u, w); for (int k = 0; k < 16; ++k) s_rw[k] = w[k]; }
+    if (threadIdx.x == 32) { u32 w[16]; chacha12_block(key, index, 3u, 0u, w); for (int k = 0; k < 16; ++k) s_e2[k] = w[k]; }
+    for (int j = threadIdx.x; j < CLUE_N; j += CLUE_THREADS) { s_pa[j] = pa[j]; s_pb[j] = pb[j]; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < CLUE_N; j += CLUE_THREADS) s_r[j] = (unsigned char)((s_rw[j >> 5] >> (j & 31)) & 1u);
+    __syncthreads();
+    // (p * r)[i] = SUM_{j<=i} p[i-j] r[j] - SUM_{j>i} p[512+i-j] r[j]   (negacyclic, mod 2048 by wrap-around of int32)
+    for (int i = threadIdx.x; i < CLUE_N; i += CLUE_THREADS) {
+        int acc = 0;
+        for (int j = 0; j <= i; ++j) acc += s_r[j] ? (int)s_pa[i - j] : 0;
+        for (int j = i + 1; j < CLUE_N; ++j) acc -= s_r[j] ? (int)s_pa[CLUE_N + i - j] : 0;
+        u32 w[16]; chacha12_block(key, index, 2u, (u32)(i >> 3), w);
+        u64 h = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if ((i & 7) == k) h = (u64)w[2 * k] | ((u64)w[2 * k + 1] << 32);
+        out_a[(size_t)blockIdx.x * CLUE_N + i] = (unsigned short)((acc + clue_gauss(h)) & (CLUE_Q - 1));
+    }
+    if (threadIdx.x < CLUE_COUNT) {
+        const int c = threadIdx.x;
+        int acc = 0;
+        for (int j = 0; j <= c; ++j) acc += s_r[j] ? (int)s_pb[c - j] : 0;
+        for (int j = c + 1; j < CLUE_N; ++j) acc -= s_r[j] ? (int)s_pb[CLUE_N + c - j] : 0;
+        const int m = msgs ? (int)(msgs[(size_t)blockIdx.x * CLUE_COUNT + c] & 7) * (CLUE_Q / 8) : 0;
+        const u64 h = (u64)s_e2[2 * c] | ((u64)s_e2[2 * c + 1] << 32);
+        out_b[(size_t)blockIdx.x * CLUE_COUNT + c] = (unsigned short)((acc + clue_gauss(h) + m) & (CLUE_Q - 1));
+    }
+}
+
+// ---- combination weights from the reference's 32-byte seed ------------------------------------------------------------------
+// detector.rs:376-387 / retriever.rs:215-226: StdRng::from_seed(seed) (rand 0.8: ChaCha12, 64-bit block counter from 0, stream
+// 0) drives Uniform::<u16>::new(0, 257).sample_iter: one u32 per draw, v * 257 = hi:lo, accept when lo <= zone (zone = 2^32 - 2:
+// one u32 value in 2^32 is rejected), weight = hi.  One thread per 64-byte ChaCha block = 16 draws.  A rejection shifts every
+// later draw, so the parallel kernel only flags it and weights_serial_kernel then regenerates the whole stream in order.
 constexpr u32 WEIGHT_ZONE = 0xFFFFFFFFu - (u32)((0xFFFFFFFFull - OUT_P + 1) % OUT_P);
 
 __global__ void weights_kernel(ChaChaKey key, size_t count, unsigned short* __restrict__ out, int* __restrict__ rejected) {
     const size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (blk * 16 >= count) return;
     u32 w[16];
-    chacha12_block(key, blk, w);
+    chacha12_block(key, blk, 0u, 0u, w);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const u64 m = (u64)w[j] * OUT_P;
@@ -1017,7 +1035,7 @@ __global__ void weights_serial_kernel(ChaChaKey key, size_t count, unsigned shor
     size_t n = 0;
     for (u64 blk = 0; n < count; ++blk) {
         u32 w[16];
-        chacha12_block(key, blk, w);
+        chacha12_block(key, blk, 0u, 0u, w);
         for (int j = 0; j < 16 && n < count; ++j) {
             const u64 m = (u64)w[j] * OUT_P;
             if ((u32)m <= WEIGHT_ZONE) out[n++] = (unsigned short)(m >> 32);

@@ -110,6 +110,8 @@ class Detector:
         if st != _lib.OMR_OK:
             raise OmrError(st, (self.L.omr_last_error(None) or b"").decode())
         self.h = h
+        if on_device:
+            pass    # omr_ctx_create_device_keys drains the device before copying (the tensors may come from any torch stream)
 
     def close(self):
         if getattr(self, "h", None):
@@ -132,6 +134,23 @@ class Detector:
 
     def launch_count(self):
         return int(self.L.omr_launch_count(self.h))
+
+    def first_level_lut(self):
+        """Detector::first_level_lut (detector.rs:117-123): u32[1024] mod q1, coefficient form"""
+        out = np.empty(N1, np.uint32); self._ck(self.L.omr_first_level_lut(self.h, out.ctypes.data)); return out
+
+    def second_level_lut(self):
+        """Detector::second_level_lut (detector.rs:126-132): u64[2048] mod q2, coefficient form"""
+        out = np.empty(N2, np.uint64); self._ck(self.L.omr_second_level_lut(self.h, out.ctypes.data)); return out
+
+    def set_output_domain(self, coeff):
+        """omr_set_output_domain: host-buffer ciphertexts in coefficient form (True; what a Rust shim uses so that nothing depends
+        on Primus-fhe's NTT ordering) or in this library's NTT ordering (False, default)"""
+        self._ck(self.L.omr_set_output_domain(self.h, _lib.OUT_COEFF if coeff else _lib.OUT_NTT_NATIVE))
+
+    def key_switch_path(self):
+        """'cuda-core' (hand-written kernels, default) or 'tensor-core' (opt-in CUTLASS int8 GEMM)"""
+        return "tensor-core" if self.L.omr_key_switch_path(self.h) else "cuda-core"
 
     def weights_from_seed(self, seed, rows, cols, in_order=False):
         """The reference's combination weights (detector.rs:376-387): StdRng::from_seed(seed) + Uniform(0, 257), rows x cols
@@ -262,9 +281,13 @@ class Detector:
         return out
 
     def gen_clues(self, clue_key, count, seed, index0=0, msgs=None):
-        """sender side (Sender::gen_clues, sender.rs:27-30) batched on the GPU: clue_key = (pa, pb) u16[512] each.
-        Returns CUDA int16 tensors (a [count][512], b [count][7])."""
+        """sender side (Sender::gen_clues, sender.rs:27-30) batched on the GPU: clue_key = (pa, pb) u16[512] each; seed = the 32
+        bytes that key the ChaCha12 stream all randomness comes from (the reference asks for a CryptoRng, clue.rs:27-30; an int
+        is widened little-endian, for tests).  Returns CUDA int16 tensors (a [count][512], b [count][7])."""
         torch = _torch()
+        seed = seed.to_bytes(32, "little") if isinstance(seed, int) else bytes(seed)
+        if len(seed) != 32:
+            raise OmrError(_lib.OMR_ERR_INVALID, "the seed is 32 bytes")
         dev = f"cuda:{self.device}"
         pa, pb = (torch.from_numpy(np.ascontiguousarray(k, np.uint16).view(np.int16)).to(dev) if not hasattr(k, "data_ptr") else k for k in clue_key)
         if pa.numel() != CLUE_N or pb.numel() != CLUE_N:
@@ -305,10 +328,14 @@ class Detector:
         return out
 
     def encode_payloads_host(self, payloads, weights, combination_count, cmb_count_per_cipher):
+        """weights [rows][D] with combination_count <= rows <= ceil(cc / per) * per: the natural [combination_count][D] matrix
+        (what Retriever._weights returns) is accepted, the library zero-fills the missing tail rows (detector.rs:370-371)."""
         payloads = np.ascontiguousarray(payloads, np.uint16).reshape(-1, PAYLOAD_LENGTH); weights = np.ascontiguousarray(weights, np.uint16)
         n_cipher = -(-combination_count // cmb_count_per_cipher)
+        if weights.ndim != 2 or not (combination_count <= weights.shape[0] <= n_cipher * cmb_count_per_cipher):
+            raise OmrError(_lib.OMR_ERR_INVALID, "weights must be [rows][D] with combination_count <= rows <= n_cipher * cmb_count_per_cipher")
         out = np.empty((n_cipher, 2, N2), np.uint64)
-        self._ck(self.L.omr_encode_payloads(self.h, payloads.ctypes.data, payloads.shape[0], weights.ctypes.data, weights.shape[1],
+        self._ck(self.L.omr_encode_payloads(self.h, payloads.ctypes.data, payloads.shape[0], weights.ctypes.data, weights.shape[0], weights.shape[1],
                                             n_cipher, cmb_count_per_cipher, out.ctypes.data))
         return out
 
