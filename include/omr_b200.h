@@ -96,6 +96,14 @@ int omr_ctx_create(int device, const omr_key_blobs* keys, omr_ctx** out);
 /* Keys already resident on `device` (same layouts); copied once more into the context's internal form.  The call drains the
  * device (cudaDeviceSynchronize) before the first copy, so the key tensors may have been produced on any stream. */
 int omr_ctx_create_device_keys(int device, const omr_key_blobs* device_keys, omr_ctx** out);
+/* SecretKeyPack::generate_detector (key_gen/secret.rs:118-187: generate_detection_key + Detector::new) with the key material
+ * made ON THE GPU: 512 + 670 RGSW encryptions, 27 648 LWE key-switching rows and 275 trace-key RLWE rows from the
+ * recipient's secrets (host arrays: s0 binary [512], z1 ternary [1024], s2 binary [670], z2 ternary [2048]) and a 32-byte seed
+ * that keys the ChaCha12 stream every mask and error is drawn from (the reference takes `R: Rng + CryptoRng`; csrc/keygen.cuh
+ * states the stream layout and the Gaussian tables).  The context is ready for detection; when host_keys_out != NULL its four
+ * buffers (layouts of omr_key_blobs, NTT-native) also receive the flat detection key — what the recipient ships to a detector. */
+typedef struct { const int32_t* s0; const int32_t* z1; const int32_t* s2; const int32_t* z2; } omr_secret_key;
+int omr_generate_detector(int device, const omr_secret_key* sk, const uint8_t* seed32, const omr_key_blobs* host_keys_out, omr_ctx** out);
 void omr_ctx_destroy(omr_ctx* ctx);
 const char* omr_last_error(const omr_ctx* ctx); /* NULL ctx -> error of the last failed create */
 /* Detector::detect_key_size (detector.rs:112-114): bytes of key material resident on the device */
@@ -119,6 +127,10 @@ int omr_detect_batch(omr_ctx* ctx, const uint16_t* clue_a, const uint16_t* clue_
                      uint64_t* pv_out, omr_stage_times* times);
 /* Forget the pertinency store (start a new bulletin board). */
 int omr_pv_reset(omr_ctx* ctx);
+/* Replace the store by pertinency ciphertexts the caller holds ([count][2][2048], in the context's output domain, global
+ * indices global_index0..) — what lets Detector::encode_pertinent_indices / encode_pertinent_payloads keep the reference's
+ * signature, which takes the pertinency vector as an argument (detector.rs:223-227, 341-351). */
+int omr_pv_load(omr_ctx* ctx, const uint64_t* pv, size_t count, uint64_t global_index0);
 /* Replaces Detector::encode_pertinent_indices (detector.rs:223-339) over the resident pertinency store, for
  * ciphertexts [cipher_idx0, cipher_idx0+n_cipher).  The reference draws buckets from thread_rng (detector.rs:262);
  * here they are a counter hash of (seed, cipher, global message index, segment), see DESIGN.md.
@@ -150,6 +162,32 @@ int omr_digest_reduce_mod(omr_ctx* ctx, uint64_t* d_words, size_t n_words, void*
  * into a running digest, acc = (acc + part) mod q2, both canonical.  Packing is a sum over messages, so a running digest
  * built batch by batch is bit-identical to packing the whole board at once. */
 int omr_digest_add_mod(omr_ctx* ctx, uint64_t* d_acc, const uint64_t* d_part, size_t n_words, void* stream);
+
+/* The same as an ingest loop with host buffers.  omr_stream_begin fixes the retrieval layout, the bucket seed of
+ * the index digest, the 32-byte rng seed of the combination weights (detector.rs:376-387) and the global index of the first
+ * message; omr_stream_push(clues, payloads, n) — any n, any number of times — detects the n next messages and folds their
+ * contributions into a RESIDENT running digest, stream-ordered behind double-buffered pinned staging (the call returns when the
+ * inputs have been staged, not when the GPU is done); omr_stream_snapshot waits for everything pushed so far and copies the
+ * digest out, [max_encode_indices_cipher_count + ceil(combination_count / cmb_count_per_cipher)][2][2048], in the context's
+ * output domain.  Identical, word for word, to omr_detect_batch + omr_encode_indices + omr_encode_payloads_seeded over the same
+ * messages in one shot.  One stream per context; it does not touch the pertinency store of omr_detect_batch. */
+int omr_stream_begin(omr_ctx* ctx, const omr_retrieval_params* rp, uint64_t index_seed, const uint8_t* weight_seed32, uint64_t global_index0);
+int omr_stream_push(omr_ctx* ctx, const uint16_t* clue_a /*[n][512]*/, const uint16_t* clue_b /*[n][7]*/, const uint16_t* payloads /*[n][612]*/, size_t n);
+int omr_stream_snapshot(omr_ctx* ctx, uint64_t* out, uint64_t* n_messages /*nullable: messages folded in so far*/);
+int omr_stream_end(omr_ctx* ctx);
+
+/* K7 — the only collective of the path: the sum over GPUs of the partial digests (the rayon
+ * reduce(add_element_wise) of detector.rs:333-336, 445-448), in place on d_digests [n_cipher][2][2048] (canonical partial
+ * digests in, their sum mod q2 out), ncclAllReduce(ncclUint64, ncclSum) + one mod-q2 kernel on `stream`.  nccl_comm is the
+ * caller's ncclComm_t (e.g. torch's), or NULL to use the context's own communicator: rank 0 draws an id with
+ * omr_comm_unique_id, hands the 128 bytes to every rank out of band, and every rank calls omr_comm_init on its context.
+ * libnccl is resolved with dlopen at first use (an already-loaded copy is preferred; OMR_NCCL_LIB overrides the name), so a
+ * single-GPU deployment does not need it; without it these calls return OMR_ERR_STATE. */
+#define OMR_COMM_ID_BYTES 128
+int omr_comm_unique_id(uint8_t* id128);
+int omr_comm_init(omr_ctx* ctx, int n_ranks, int rank, const uint8_t* id128);
+int omr_comm_destroy(omr_ctx* ctx);
+int omr_digest_allreduce(omr_ctx* ctx, void* nccl_comm, uint64_t* d_digests, size_t n_cipher, void* stream);
 
 /* Recipient side (Retriever::decode_pertinent_indices / decode_combined_payloads, retriever.rs:63-130,
  * 318-362): decrypt n NTT-domain RLWE ciphertexts with the recipient's NTT-domain secret z2 (b - a*z2, inverse NTT) and

@@ -550,6 +550,115 @@ inline DetectionKey gen_detection_key(const SecretKeyPack& sk, u64 seed) {
     return dk;
 }
 
+// Counter-based detection-key generation: the same keys as gen_detection_key (secret.rs:118-178), but every draw
+// comes from ChaCha12 keyed by a 32-byte seed in counter mode (the reference requires a CryptoRng), so that the CUDA key generator
+// (csrc/keygen.cuh) can be checked bit for bit.  Stream layout — block(counter, nonce = (domain, 0)):
+//   domains 16/17 = BSK1 masks/errors, 18/19 = KSK, 20/21 = BSK2, 22/23 = trace key;
+//   mask element e (flat index into the a-parts, NTT order; KSK: row * 672 + k): block e / 4, four words per element: q1 takes the first
+//     of four 27-bit candidates below q1, q2 the first of two 50-bit candidates (lo | hi << 32); all rejected -> last one minus q;
+//   error e (flat index, coefficient order; KSK: the row): block e / 8, h = w[2(e%8)] | w[2(e%8)+1] << 32; rounded Gaussian from an
+//     integer cumulative table on the low 32 bits, sign = bit 63; KSK: 512 x + ((h >> 32) & 511) - 256 with x of sigma 4.0556.
+static const u32 KG_CDT_L1[21] = {535621359u, 1555783112u, 2436857004u, 3126965323u, 3617176249u, 3932973494u, 4117471559u, 4215224899u,
+                                  4262195442u, 4282663250u, 4290751715u, 4293650440u, 4294592526u, 4294870186u, 4294944398u, 4294962385u,
+                                  4294966338u, 4294967126u, 4294967269u, 4294967292u, 4294967295u};     // sigma 3.1859
+static const u32 KG_CDT_L2[3] = {3432766375u, 4294435154u, 4294967295u};                               // sigma 0.3908
+static const u32 KG_CDT_KS[26] = {421424793u, 1239163273u, 1985968725u, 2627960021u, 3147452532u, 3543144983u, 3826848252u, 4018317373u,
+                                  4139952964u, 4212689020u, 4253630692u, 4275323096u, 4286141809u, 4291220698u, 4293465027u, 4294398558u,
+                                  4294764063u, 4294898767u, 4294945497u, 4294960755u, 4294965445u, 4294966802u, 4294967172u, 4294967267u,
+                                  4294967289u, 4294967295u};                                           // sigma 4.0556 (x 512 + uniform = 2081.7)
+struct CbStream {                       // one (key, domain): cached current block
+    u32 key[8]; u32 domain; u64 cur = ~0ull; u32 w[16];
+    CbStream(const u8 seed[32], u32 dom) : domain(dom) { seed_to_key(seed, key); }
+    const u32* block(u64 b) { if (b != cur) { chacha_block(key, b, (u64)domain, 12, w); cur = b; } return w; }
+    u64 draw64(u64 e) { const u32* x = block(e >> 3); return (u64)x[2 * (e & 7)] | ((u64)x[2 * (e & 7) + 1] << 32); }
+    u32 uniform_q1(u64 e) {
+        const u32* x = block(e >> 2) + 4 * (e & 3);
+        for (int c = 0; c < 3; ++c) { u32 v = x[c] & ((1u << 27) - 1); if (v < Q1) return v; }
+        u32 v = x[3] & ((1u << 27) - 1); return v >= Q1 ? v - Q1 : v;
+    }
+    u64 uniform_q2(u64 e) {
+        const u32* x = block(e >> 2) + 4 * (e & 3);
+        const u64 c0 = ((u64)x[0] | ((u64)x[1] << 32)) & ((1ull << 50) - 1), c1 = ((u64)x[2] | ((u64)x[3] << 32)) & ((1ull << 50) - 1);
+        const u64 v = c0 < Q2 ? c0 : c1; return v >= Q2 ? v - Q2 : v;
+    }
+};
+template <int LEN> inline i32 cdt_gauss(const u32 (&cdt)[LEN], u64 h) {
+    const u32 u = (u32)h; i32 m = 0;
+    for (int k = 0; k < LEN; ++k) m += u >= cdt[k];
+    return (h >> 63) ? -m : m;
+}
+// one RLWE row of a key array: a uniform (NTT order), e Gaussian (coefficient order) -> NTT, b = a z + e + msg
+template <class T, int LEN>
+inline void rlwe_row_cb(const NttTable<T>& tab, const T* z_ntt, const T* msg_ntt, const u32 (&cdt)[LEN], CbStream& sa, CbStream& se, u64 row,
+                        T* a_out, T* b_out) {
+    const int n = tab.n; const T q = tab.q;
+    std::vector<T> e(n);
+    for (int i = 0; i < n; ++i) e[i] = signed_to_field<T>(cdt_gauss(cdt, se.draw64(row * n + i)), q);
+    tab.forward(e.data());
+    for (int i = 0; i < n; ++i) {
+        const u64 el = row * n + i;
+        T a; if constexpr (sizeof(T) == 4) a = sa.uniform_q1(el); else a = sa.uniform_q2(el);
+        a_out[i] = a;
+        b_out[i] = addmod(addmod(mulmod(a, z_ntt[i], q), e[i], q), msg_ntt[i], q);
+    }
+}
+template <class T, int LEN>
+inline void rgsw_rows_cb(const NttTable<T>& tab, const T* z_ntt, int m, int logb, int levels, int drop, const u32 (&cdt)[LEN],
+                         CbStream& sa, CbStream& se, u64 row0, T* out /*[2*levels][2][n]*/) {
+    const int n = tab.n; const T q = tab.q;
+    std::vector<T> msg(n);
+    for (int row = 0; row < 2 * levels; ++row) {
+        const T gm = m ? powmod<T>(2, (u64)(drop + logb * (row % levels)), q) : 0;
+        for (int i = 0; i < n; ++i) msg[i] = row < levels ? submod((T)0, mulmod(z_ntt[i], gm, q), q) : gm;
+        rlwe_row_cb<T, LEN>(tab, z_ntt, msg.data(), cdt, sa, se, row0 + row, out + ((size_t)row * 2) * n, out + ((size_t)row * 2 + 1) * n);
+    }
+}
+inline DetectionKey gen_detection_key_cb(const SecretKeyPack& sk, const u8 seed[32]) {
+    const Tables& tb = tables();
+    DetectionKey dk;
+    std::vector<u32> z1n(N1);
+    for (int i = 0; i < N1; ++i) z1n[i] = signed_to_field<u32>(sk.z1[i], Q1);
+    tb.t1.forward(z1n.data());
+    dk.bsk1.resize(BSK1_ELEMS);
+    { CbStream sa(seed, 16), se(seed, 17);
+      for (int i = 0; i < CLUE_N; ++i)
+          rgsw_rows_cb<u32, 21>(tb.t1, z1n.data(), sk.s0[i], BS1_LOGB, BS1_LEVELS, BS1_DROP, KG_CDT_L1, sa, se, (u64)i * BSK1_ROWS,
+                                dk.bsk1.data() + (size_t)i * BSK1_ROWS * 2 * N1); }
+    dk.ksk.resize(KSK_ELEMS);
+    { CbStream sa(seed, 18), se(seed, 19);
+      for (int i = 0; i < N1; ++i) for (int j = 0; j < KS_LEVELS; ++j) {
+          const u64 r = (u64)i * KS_LEVELS + j;
+          u32* row = dk.ksk.data() + r * KSK_STRIDE;
+          u64 dot = 0;
+          for (int k = 0; k < LWE2_N; ++k) { row[k] = sa.uniform_q1(r * 672 + k); if (sk.s2[k]) dot += row[k]; }
+          const u64 h = se.draw64(r);
+          const i64 e = (i64)512 * cdt_gauss(KG_CDT_KS, h) + (i64)((h >> 32) & 511) - 256;
+          const u32 m = mulmod(signed_to_field<u32>(sk.z1[i], Q1), powmod<u32>(2, j, Q1), Q1);
+          row[LWE2_N] = addmod(addmod((u32)(dot % Q1), signed_to_field<u32>(e, Q1), Q1), m, Q1);
+      } }
+    dk.bsk2.resize(BSK2_ELEMS);
+    { CbStream sa(seed, 20), se(seed, 21);
+      for (int i = 0; i < LWE2_N; ++i)
+          rgsw_rows_cb<u64, 3>(tb.t2, sk.z2_ntt.data(), sk.s2[i], BS2_LOGB, BS2_LEVELS, BS2_DROP, KG_CDT_L2, sa, se, (u64)i * BSK2_ROWS,
+                               dk.bsk2.data() + (size_t)i * BSK2_ROWS * 2 * N2); }
+    dk.trk.resize(TRK_ELEMS);
+    { CbStream sa(seed, 22), se(seed, 23);
+      std::vector<u64> zc(N2), zs(N2), msg(N2);
+      for (int i = 0; i < N2; ++i) zc[i] = signed_to_field<u64>(sk.z2[i], Q2);
+      for (int t = 0; t < TR_STEPS; ++t) {
+          const int d = (1 << (TR_STEPS - t)) + 1;
+          automorphism<u64>(zc.data(), N2, d, Q2, zs.data());
+          tb.t2.forward(zs.data());
+          for (int j = 0; j < TR_LEVELS; ++j) {
+              const u64 g = powmod<u64>(2, (u64)(TR_DROP + TR_LOGB * j), Q2);
+              for (int i = 0; i < N2; ++i) msg[i] = submod((u64)0, mulmod(zs[i], g, Q2), Q2);
+              u64* row = dk.trk.data() + ((size_t)t * TR_LEVELS + j) * 2 * N2;
+              rlwe_row_cb<u64, 3>(tb.t2, sk.z2_ntt.data(), msg.data(), KG_CDT_L2, sa, se, (u64)t * TR_LEVELS + j, row, row + N2);
+          }
+      } }
+    return dk;
+}
+
 // ---------------------------------------------------------------------------
 // The hot path.
 // ---------------------------------------------------------------------------

@@ -91,6 +91,14 @@ void* orc_key_from_blobs(const uint32_t* bsk1, const uint32_t* ksk, const uint64
     h->dk.bsk2.assign(bsk2, bsk2 + BSK2_ELEMS); h->dk.trk.assign(trk, trk + TRK_ELEMS);
     return h;
 }
+// the same secrets (and clue key) with a detection key from the counter-based generator (bit-exact twin of csrc/keygen.cuh)
+void* orc_keygen_cb(void* hh, const uint8_t* seed32) {
+    auto* src = (OrcHandle*)hh;
+    auto* h = new OrcHandle;
+    h->sk = src->sk; h->ck = src->ck; h->has_secret = true;
+    h->dk = gen_detection_key_cb(h->sk, seed32);
+    return h;
+}
 void orc_free(void* h) { delete (OrcHandle*)h; }
 const uint32_t* orc_bsk1(void* h) { return ((OrcHandle*)h)->dk.bsk1.data(); }
 const uint32_t* orc_ksk(void* h) { return ((OrcHandle*)h)->dk.ksk.data(); }

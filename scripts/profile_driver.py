@@ -11,11 +11,11 @@ from stage_times import random_detector
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=8192)
 ap.add_argument("--board", type=int, default=65536)
-ap.add_argument("--cuda-core-ks", action="store_true")
+ap.add_argument("--tensor-core-ks", action="store_true", help="opt into the CUTLASS int8 GEMM key switch (default: hand-written CUDA-core kernels)")
 args = ap.parse_args()
 det = random_detector()
-if args.cuda_core_ks:
-    det.set_tensor_core_key_switch(False)
+if args.tensor_core_ks:
+    det.set_tensor_core_key_switch(True)
 B = args.batch
 g = torch.Generator(device="cuda"); g.manual_seed(B)
 a = torch.randint(0, 2048, (B, 512), dtype=torch.int16, device="cuda", generator=g)

@@ -50,6 +50,7 @@ def lib(native=False):
     L.orc_keygen.restype = vp; L.orc_keygen.argtypes = [u64]
     L.orc_keygen_sender_only.restype = vp; L.orc_keygen_sender_only.argtypes = [u64]
     L.orc_key_from_blobs.restype = vp; L.orc_key_from_blobs.argtypes = [vp, vp, vp, vp]
+    L.orc_keygen_cb.restype = vp; L.orc_keygen_cb.argtypes = [vp, C.c_char_p]
     L.orc_free.argtypes = [vp]
     for nm in ("orc_bsk1", "orc_ksk", "orc_bsk2", "orc_trk"):
         getattr(L, nm).restype = vp; getattr(L, nm).argtypes = [vp]
@@ -112,9 +113,12 @@ def _view(addr, shape, dtype):
 class KeyPack:
     """SecretKeyPack + ClueKey + DetectionKey of the oracle (key_gen/secret.rs)."""
 
-    def __init__(self, seed=None, sender_only=False, blobs=None, native=False):
+    def __init__(self, seed=None, sender_only=False, blobs=None, native=False, cb_from=None, cb_seed=None):
         self.L = lib(native)
-        if blobs is not None:
+        if cb_from is not None:                       # same secrets / clue key, detection key from the counter-based generator
+            assert len(cb_seed) == 32
+            self.h = self.L.orc_keygen_cb(cb_from.h, bytes(cb_seed))
+        elif blobs is not None:
             self._blobs = [np.ascontiguousarray(b) for b in blobs]
             self.h = self.L.orc_key_from_blobs(*[ptr(b) for b in self._blobs])
         elif sender_only:

@@ -47,6 +47,10 @@ def test_coefficient_domain_outputs(detector, keypack, small):
         pay_c = detector.encode_payloads_seeded_host(payloads, seed, D, rp.combination_count, 2)
         assert np.array_equal(pv_c, _intt2(pv_ntt))
         assert np.array_equal(idx_c, _intt2(idx_ntt)) and np.array_equal(pay_c, _intt2(pay_ntt))
+        # the reference's signatures hand the pertinency vector back in (detector.rs:223-227): load it, pack again
+        detector.pv_load(pv_c, global_index0=100)
+        assert np.array_equal(detector.encode_indices_host(rp, 11, 0, rp.max_encode_indices_cipher_count), idx_c)
+        assert np.array_equal(detector.encode_payloads_seeded_host(payloads, seed, D, rp.combination_count, 2), pay_c)
         # a coefficient-domain pertinency ciphertext decrypts with the plain secret: b - a*z2 = Delta * [1,0,...] (omd.rs:45-58)
         s0, z1, s2, z2 = keypack.secrets()
         z2c = np.where(z2 < 0, O.Q2 + z2.astype(np.int64), z2.astype(np.int64)).astype(np.uint64)
@@ -144,3 +148,87 @@ def test_calls_restore_the_current_device(detector, small):
         d1.detect_host(a[:1], b[:1])
         assert torch.cuda.current_device() == before
         d1.close()
+
+
+def test_stream_push_equals_one_shot(detector, keypack, decoy):
+    """an ingest loop with arbitrary push sizes (crossing the 4 096-message staging chunk) builds the same
+    resident digest, word for word, as detect + encode over the same messages in one shot — and it decodes."""
+    import tfhe_omr_b200 as omr
+    n, D, index0 = 4300, 6000, 1000
+    rng = np.random.default_rng(8)
+    a, b = decoy.gen_clues(41, n, threads=16)
+    planted = np.sort(rng.choice(n, 5, replace=False))
+    pa, pb = keypack.gen_clues(42, len(planted), threads=8)
+    a[planted], b[planted] = pa, pb
+    payloads = rng.integers(0, 256, (n, O.PAYLOAD_LEN), dtype=np.uint16)
+    rp = omr.RetrievalParams(D, len(planted))
+    seed = bytes(range(7, 39))
+    detector.pv_reset()
+    detector.detect_host(a, b, global_index0=index0)
+    want = np.concatenate([detector.encode_indices_host(rp, 0x5EED, 0, rp.max_encode_indices_cipher_count),
+                           detector.encode_payloads_seeded_host(payloads, seed, D, rp.combination_count, rp.cmb_count_per_cipher)])
+    detector.pv_reset()
+    detector.stream_begin(rp, 0x5EED, seed, global_index0=index0)
+    got0, n0 = detector.stream_snapshot()
+    assert n0 == 0 and not got0.any()
+    lo = 0
+    for sz in (1, 0, 7, 4097, 2, 193):
+        detector.stream_push(a[lo:lo + sz], b[lo:lo + sz], payloads[lo:lo + sz]); lo += sz
+    assert lo == n
+    got, cnt = detector.stream_snapshot()
+    assert cnt == n and np.array_equal(got, want)
+    with pytest.raises(omr.OmrError):                                   # the board is full after D - index0 messages
+        detector.stream_push(a[:D - index0 - n + 1], b[:D - index0 - n + 1], payloads[:D - index0 - n + 1])
+    detector.stream_end()
+    with pytest.raises(omr.OmrError):
+        detector.stream_push(a[:1], b[:1], payloads[:1])
+    s0, z1, s2, z2 = keypack.secrets()
+    z2n = np.where(z2 < 0, O.Q2 + z2.astype(np.int64), z2.astype(np.int64)).astype(np.uint64)
+    O.lib().orc_ntt2_forward(O.ptr(z2n), 1)
+    n_idx = rp.max_encode_indices_cipher_count
+    found, solved = omr.Retriever(detector, rp, z2n).decode_digest_host(got[:n_idx], got[n_idx:], seed=seed)
+    assert found == [index0 + int(p) for p in planted] and np.array_equal(solved, payloads[planted])
+
+
+def test_digest_allreduce_single_rank(detector):
+    """K7 through the C ABI with the library's own communicator (one rank: the sum is the identity, the mod-q2 pass is not)"""
+    import torch
+    import tfhe_omr_b200 as omr
+    try:
+        uid = detector.comm_unique_id()
+    except omr.OmrError as e:
+        pytest.skip(f"libnccl not loadable here: {e}")
+    detector.comm_init(1, 0, uid)
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    x = torch.randint(0, 2**62, (33, 2, 2048), dtype=torch.int64, device="cuda", generator=g)
+    want = (x.cpu().numpy().view(np.uint64) % np.uint64(O.Q2))
+    detector.digest_allreduce(x); torch.cuda.synchronize()
+    assert np.array_equal(x.cpu().numpy().view(np.uint64), want)
+    detector.comm_destroy()
+    with pytest.raises(omr.OmrError):
+        detector.digest_allreduce(x)
+
+
+def test_gpu_detection_key_generation(keypack, decoy):
+    """SURVEY §8f.4 / secret.rs:118-178: the detection key made on the GPU from the recipient's secrets and a 32-byte seed is,
+    word for word, the oracle's counter-based key (BSK1, KSK, BSK2, trace key), and a detector made that way passes the
+    reference's omd assertions (omd.rs:45-58) on clues of the same recipient."""
+    import tfhe_omr_b200 as omr
+    seed = bytes(range(200, 232))
+    det = omr.Detector.generate(keypack.secrets(), seed, device=0, want_keys=True)
+    ref = O.KeyPack(cb_from=keypack, cb_seed=seed)
+    dk = det.detection_key
+    for name, got, want in (("bsk1", dk.bsk1, ref.bsk1), ("ksk", dk.ksk, ref.ksk), ("bsk2", dk.bsk2, ref.bsk2), ("trace", dk.trace, ref.trk)):
+        assert got.shape == want.shape and np.array_equal(got, want), name
+    assert dk.bsk1.max() < O.Q1 and dk.ksk.max() < O.Q1 and dk.bsk2.max() < O.Q2 and dk.trace.max() < O.Q2
+    a0, b0 = keypack.gen_clues(901, 2)
+    a1, b1 = decoy.gen_clues(902, 2)
+    a, b = np.concatenate([a0, a1]), np.concatenate([b0, b1])
+    pv = det.detect((a, b)).to_host()
+    assert np.array_equal(pv, ref.detect(a, b, threads=4))                 # same key on both sides -> same ciphertexts
+    dec = [keypack.decrypt_decode(pv[i]) for i in range(4)]
+    assert all(d[0] == 1 and not d[1:].any() for d in dec[:2]) and all(not d.any() for d in dec[2:])
+    with pytest.raises(omr.OmrError):                                      # secrets are validated
+        s0, z1, s2, z2 = keypack.secrets()
+        omr.Detector.generate((s0 + 2, z1, s2, z2), seed, device=0)
+    det.close()

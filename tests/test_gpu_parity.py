@@ -75,7 +75,7 @@ def test_launch_shapes_agree(detector, keypack):
     rl = rng.integers(0, O.Q1, (256, 2, O.N1), dtype=np.uint32)
     lw = rng.integers(0, 4096, (300, 671), dtype=np.uint32)
     got = {}
-    detector.set_tensor_core_key_switch(False)              # compare the CUDA-core key-switch shapes with each other
+    assert detector.key_switch_path() == "cuda-core"        # compare the (default) CUDA-core key-switch shapes with each other
     for lat in (True, False):
         detector.set_latency_shapes(lat)
         l1 = [detector.first_level_blind_rotate(_dev(a[:n], np.int16), _dev(b[:n], np.int16)) for n in (21, 22, 43, 100, 200)]
@@ -84,7 +84,6 @@ def test_launch_shapes_agree(detector, keypack):
         torch.cuda.synchronize()
         got[lat] = [x.cpu().numpy() for x in l1 + ks + l2]
     detector.set_latency_shapes(True)
-    detector.set_tensor_core_key_switch(True)
     for x, y in zip(got[True], got[False]):
         assert np.array_equal(x, y)
     # key switch of one message against the oracle on a random (full-range) ciphertext
@@ -103,7 +102,7 @@ def test_small_batch_exchanges_repeatable(detector):
     lw = rng.integers(0, 4096, (44, 671), dtype=np.uint32)
     rl = rng.integers(0, O.Q1, (40, 2, O.N1), dtype=np.uint32)
     da, db, dlw, drl = _dev(a, np.int16), _dev(b, np.int16), _dev(lw, np.int32), _dev(rl, np.int32)
-    detector.set_tensor_core_key_switch(False)              # the CUDA-core key switch with its integer atomics is the one under test
+    assert detector.key_switch_path() == "cuda-core"        # the CUDA-core key switch with its integer atomics is the one under test
     detector.set_latency_shapes(False)
     want = [detector.first_level_blind_rotate(da, db), detector.second_level_blind_rotate(dlw[:22]), detector.second_level_blind_rotate(dlw),
             detector.key_switch(drl)]
@@ -115,7 +114,6 @@ def test_small_batch_exchanges_repeatable(detector):
         torch.cuda.synchronize()
         for x, y in zip(got, want):
             assert torch.equal(x, y)
-    detector.set_tensor_core_key_switch(True)
 
 
 def test_extreme_inputs_bit_exact(detector, keypack, shape):

@@ -18,12 +18,19 @@ EXPORTS = [
     "omr_l1_blind_rotate_device", "omr_keyswitch_device", "omr_l2_blind_rotate_device", "omr_trace_device",
     "omr_ntt_forward_device", "omr_ntt_inverse_device", "omr_launch_count", "omr_mulmod_peak", "omr_digest_add_mod", "omr_decrypt_decode_device", "omr_gen_clues_device", "omr_set_latency_shapes", "omr_decode_digest", "omr_weights_from_seed_device", "omr_encode_payloads_seeded", "omr_set_tensor_core_key_switch",
     "omr_blob_field_count", "omr_blob_field_bytes", "omr_blob_write", "omr_blob_read_header", "omr_blob_read", "omr_ctx_create_from_blob",
+    "omr_stream_begin", "omr_stream_push", "omr_stream_snapshot", "omr_stream_end",
+    "omr_comm_unique_id", "omr_comm_init", "omr_comm_destroy", "omr_digest_allreduce",
+    "omr_generate_detector", "omr_pv_load",
     "omr_first_level_lut", "omr_second_level_lut", "omr_set_output_domain", "omr_key_switch_path",
 ]
 
 
 class KeyBlobs(C.Structure):
     _fields_ = [("bsk1", C.c_void_p), ("ksk", C.c_void_p), ("bsk2", C.c_void_p), ("trace", C.c_void_p), ("flags", C.c_uint32)]
+
+
+class SecretKey(C.Structure):
+    _fields_ = [("s0", C.c_void_p), ("z1", C.c_void_p), ("s2", C.c_void_p), ("z2", C.c_void_p)]
 
 
 class StageTimes(C.Structure):
@@ -71,6 +78,7 @@ def load():
     L.omr_retrieval_params_init.restype = i32; L.omr_retrieval_params_init.argtypes = [u64, u32, P(RetrievalParamsC)]
     L.omr_detect_batch.restype = i32; L.omr_detect_batch.argtypes = [vp, vp, vp, sz, u64, vp, P(StageTimes)]
     L.omr_pv_reset.restype = i32; L.omr_pv_reset.argtypes = [vp]
+    L.omr_pv_load.restype = i32; L.omr_pv_load.argtypes = [vp, vp, sz, u64]
     L.omr_encode_indices.restype = i32; L.omr_encode_indices.argtypes = [vp, P(RetrievalParamsC), u64, u32, u32, vp]
     L.omr_encode_payloads.restype = i32; L.omr_encode_payloads.argtypes = [vp, vp, sz, vp, sz, sz, u32, u32, vp]
     L.omr_detect_batch_device.restype = i32; L.omr_detect_batch_device.argtypes = [vp, vp, vp, sz, vp, vp, P(StageTimes)]
@@ -94,6 +102,15 @@ def load():
     L.omr_blob_read_header.restype = i32; L.omr_blob_read_header.argtypes = [C.c_char_p, P(BlobHeader)]
     L.omr_blob_read.restype = i32; L.omr_blob_read.argtypes = [C.c_char_p, P(BlobHeader), P(vp), u32]
     L.omr_ctx_create_from_blob.restype = i32; L.omr_ctx_create_from_blob.argtypes = [i32, C.c_char_p, P(vp)]
+    L.omr_stream_begin.restype = i32; L.omr_stream_begin.argtypes = [vp, P(RetrievalParamsC), u64, C.c_char_p, u64]
+    L.omr_stream_push.restype = i32; L.omr_stream_push.argtypes = [vp, vp, vp, vp, sz]
+    L.omr_stream_snapshot.restype = i32; L.omr_stream_snapshot.argtypes = [vp, vp, P(u64)]
+    L.omr_stream_end.restype = i32; L.omr_stream_end.argtypes = [vp]
+    L.omr_comm_unique_id.restype = i32; L.omr_comm_unique_id.argtypes = [vp]
+    L.omr_comm_init.restype = i32; L.omr_comm_init.argtypes = [vp, i32, i32, vp]
+    L.omr_comm_destroy.restype = i32; L.omr_comm_destroy.argtypes = [vp]
+    L.omr_digest_allreduce.restype = i32; L.omr_digest_allreduce.argtypes = [vp, vp, vp, sz, vp]
+    L.omr_generate_detector.restype = i32; L.omr_generate_detector.argtypes = [i32, P(SecretKey), C.c_char_p, P(KeyBlobs), P(vp)]
     L.omr_first_level_lut.restype = i32; L.omr_first_level_lut.argtypes = [vp, vp]
     L.omr_second_level_lut.restype = i32; L.omr_second_level_lut.argtypes = [vp, vp]
     L.omr_set_output_domain.restype = i32; L.omr_set_output_domain.argtypes = [vp, u32]

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "lib", "libomr_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("capi.cu", "ks_gemm.cu", "blob.cu", "kernels.cuh", "ntt.cuh", "field.cuh")] + \
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("capi.cu", "ks_gemm.cu", "blob.cu", "nccl_dl.cu", "nccl_dl.hpp", "kernels.cuh", "ntt.cuh", "field.cuh")] + \
           [os.path.join(ROOT, "include", "omr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
     extra = ["-DOMR_HAVE_CUTLASS", "--expt-relaxed-constexpr", "-diag-suppress", "20012", "-I" + os.path.join(cutlass, "include"),
              "-I" + os.path.join(cutlass, "tools", "util", "include")] if cutlass else []
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [s for s in SOURCES if s.endswith(".cu")]
+          ["-o", LIB] + [s for s in SOURCES if s.endswith(".cu")] + ["-ldl"]
     subprocess.check_call(cmd, cwd=HERE)
     return LIB
 

@@ -2,6 +2,8 @@
 // compute entry point launches CUDA kernels or returns OMR_ERR_CUDA.
 #include "../../include/omr_b200.h"
 #include "kernels.cuh"
+#include "keygen.cuh"
+#include "nccl_dl.hpp"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -83,7 +85,17 @@ struct omr_ctx {
     uint32_t out_domain = OMR_OUT_NTT_NATIVE;     // omr_set_output_domain: domain of host-buffer ciphertexts
     u64* s_coeff = nullptr; size_t coeff_words = 0;   // staging for coefficient-domain copies of pertinency ciphertexts
     std::vector<u32> h_lut1; std::vector<u64> h_lut2; // host copies of the test vectors (omr_first_level_lut / omr_second_level_lut)
+    void* comm = nullptr;                             // own NCCL communicator (omr_comm_init), K7
+    // streaming ingest (omr_stream_*): resident running digest + double-buffered pinned staging
+    struct Stream {
+        bool active = false; omr_retrieval_params rp{}; u64 index_seed = 0; u64 index0 = 0, count = 0; uint32_t n_idx = 0, n_pay = 0;
+        u64* digest = nullptr; u64* part = nullptr; u64* pv = nullptr; unsigned short* weights = nullptr; size_t weight_elems = 0;
+        unsigned char* pinned[2] = {nullptr, nullptr}; unsigned char* dev[2] = {nullptr, nullptr}; cudaEvent_t copied[2] = {nullptr, nullptr};
+        int next = 0;
+    } st;
 };
+constexpr size_t STREAM_CHUNK = 4096;                                        // messages per staged chunk
+constexpr size_t STREAM_MSG_BYTES = (CLUE_N + CLUE_COUNT + PAYLOAD_LEN) * 2; // clue a, clue b, payload
 
 namespace omr {            // ks_gemm.cu: the key switch as an int8 tensor-core GEMM (a CUTLASS template instance; opt-in), if it was compiled in
 int ks_gemm_i8(const int8_t* A, const int8_t* B, int32_t* C, int M, int N, int K, void* workspace, size_t workspace_bytes, cudaStream_t s);
@@ -318,9 +330,25 @@ int ensure_digest(omr_ctx* ctx, size_t words) {
     return OMR_OK;
 }
 
-int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_ctx** out) {
-    if (!keys || !out || !keys->bsk1 || !keys->ksk || !keys->bsk2 || !keys->trace) { g_create_error = "null argument"; return OMR_ERR_INVALID; }
-    if (keys->flags != OMR_KEYS_NTT_NATIVE && keys->flags != OMR_KEYS_COEFF) { g_create_error = "unknown key flags"; return OMR_ERR_INVALID; }
+void stream_release(omr_ctx* ctx) {
+    auto& st = ctx->st;
+    cudaFree(st.digest); cudaFree(st.part); cudaFree(st.pv); cudaFree(st.weights);
+    for (int i = 0; i < 2; ++i) { if (st.pinned[i]) cudaFreeHost(st.pinned[i]); cudaFree(st.dev[i]); if (st.copied[i]) cudaEventDestroy(st.copied[i]); }
+    st = omr_ctx::Stream{};
+}
+
+// detection-key generation request (omr_generate_detector): the key is made on the device and loaded from there
+struct KeygenSpec { const omr_secret_key* sk; const uint8_t* seed32; const omr_key_blobs* host_out; };
+struct DevBufs {           // temporaries freed on every return path
+    std::vector<void*> p;
+    template <class T> cudaError_t alloc(T** q, size_t n) { cudaError_t e = cudaMalloc((void**)q, n * sizeof(T)); if (e == cudaSuccess) p.push_back(*q); return e; }
+    ~DevBufs() { for (void* q : p) cudaFree(q); }
+};
+
+int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_ctx** out, const KeygenSpec* gen = nullptr) {
+    if (!out || (!gen && (!keys || !keys->bsk1 || !keys->ksk || !keys->bsk2 || !keys->trace))) { g_create_error = "null argument"; return OMR_ERR_INVALID; }
+    if (!gen && keys->flags != OMR_KEYS_NTT_NATIVE && keys->flags != OMR_KEYS_COEFF) { g_create_error = "unknown key flags"; return OMR_ERR_INVALID; }
+    if (gen && (!gen->sk || !gen->seed32 || !gen->sk->s0 || !gen->sk->z1 || !gen->sk->s2 || !gen->sk->z2)) { g_create_error = "null argument"; return OMR_ERR_INVALID; }
     *out = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -432,8 +460,46 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
     CKC(cudaMalloc((void**)&ctx->bsk1, n_bsk1 * 4)); CKC(cudaMalloc((void**)&ctx->ksk, n_ksk_rows * KSK_PAD * 4));
     CKC(cudaMalloc((void**)&ctx->bsk2, n_bsk2 * 8)); CKC(cudaMalloc((void**)&ctx->trk, n_trk * 8));
     ctx->key_bytes = n_bsk1 * 4 + n_ksk_rows * KSK_PAD * 4 + n_bsk2 * 8 + n_trk * 8;
-    const cudaMemcpyKind kind = keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     cudaStream_t s = ctx->stream;
+    DevBufs tmp_bufs; omr_key_blobs gen_blobs{};
+    if (gen) {
+        // SecretKeyPack::generate_detection_key (secret.rs:118-178) on the device, into flat NTT-native blobs
+        for (int i = 0; i < CLUE_N; ++i) if (gen->sk->s0[i] != 0 && gen->sk->s0[i] != 1) { ctx->err = "keygen: s0 must be binary"; return fail(OMR_ERR_INVALID); }
+        for (int i = 0; i < LWE2_N; ++i) if (gen->sk->s2[i] != 0 && gen->sk->s2[i] != 1) { ctx->err = "keygen: s2 must be binary"; return fail(OMR_ERR_INVALID); }
+        for (int i = 0; i < F1::N; ++i) if (gen->sk->z1[i] < -1 || gen->sk->z1[i] > 1) { ctx->err = "keygen: z1 must be ternary"; return fail(OMR_ERR_INVALID); }
+        for (int i = 0; i < F2::N; ++i) if (gen->sk->z2[i] < -1 || gen->sk->z2[i] > 1) { ctx->err = "keygen: z2 must be ternary"; return fail(OMR_ERR_INVALID); }
+        u32 *g_bsk1 = nullptr, *g_ksk = nullptr, *d_z1n = nullptr; u64 *g_bsk2 = nullptr, *g_trk = nullptr, *d_z2c = nullptr, *d_z2n = nullptr, *d_zs = nullptr;
+        i32 *d_s0 = nullptr, *d_z1 = nullptr, *d_s2 = nullptr, *d_z2 = nullptr;
+        CKC(tmp_bufs.alloc(&g_bsk1, n_bsk1)); CKC(tmp_bufs.alloc(&g_ksk, n_ksk_rows * LWE2_STRIDE_IN));
+        CKC(tmp_bufs.alloc(&g_bsk2, n_bsk2)); CKC(tmp_bufs.alloc(&g_trk, n_trk));
+        CKC(tmp_bufs.alloc(&d_s0, (size_t)CLUE_N)); CKC(tmp_bufs.alloc(&d_z1, (size_t)F1::N)); CKC(tmp_bufs.alloc(&d_s2, (size_t)LWE2_N)); CKC(tmp_bufs.alloc(&d_z2, (size_t)F2::N));
+        CKC(tmp_bufs.alloc(&d_z1n, (size_t)F1::N)); CKC(tmp_bufs.alloc(&d_z2c, (size_t)F2::N)); CKC(tmp_bufs.alloc(&d_z2n, (size_t)F2::N)); CKC(tmp_bufs.alloc(&d_zs, (size_t)TR_STEPS * F2::N));
+        CKC(cudaMemcpyAsync(d_s0, gen->sk->s0, CLUE_N * 4, cudaMemcpyHostToDevice, s)); CKC(cudaMemcpyAsync(d_z1, gen->sk->z1, F1::N * 4, cudaMemcpyHostToDevice, s));
+        CKC(cudaMemcpyAsync(d_s2, gen->sk->s2, LWE2_N * 4, cudaMemcpyHostToDevice, s)); CKC(cudaMemcpyAsync(d_z2, gen->sk->z2, F2::N * 4, cudaMemcpyHostToDevice, s));
+        const ChaChaKey ck = chacha_key_from_seed(gen->seed32);
+        kg_lift_kernel<F1><<<(F1::N + 255) / 256, 256, 0, s>>>(d_z1, d_z1n, F1::N);
+        kg_lift_kernel<F2><<<(F2::N + 255) / 256, 256, 0, s>>>(d_z2, d_z2c, F2::N);
+        CKC(cudaMemcpyAsync(d_z2n, d_z2c, F2::N * 8, cudaMemcpyDeviceToDevice, s));
+        kg_automorph_kernel<<<dim3((F2::N + 255) / 256, TR_STEPS), 256, 0, s>>>(d_z2c, d_zs);
+        ntt_kernel<F1, false><<<1, ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>(d_z1n, tb, ctx->n1_inv);
+        ntt_kernel<F2, false><<<1, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(d_z2n, tb, ctx->n2_inv);
+        ntt_kernel<F2, false><<<TR_STEPS, ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(d_zs, tb, ctx->n2_inv);
+        kg_rlwe_rows_kernel<F1, G1, 0, 21><<<(unsigned)(CLUE_N * 2 * G1::LEVELS), ntt_kernel_threads<F1>(), ntt_kernel_smem<F1>(), s>>>(ck, KG_BSK1_A, KG_BSK1_E, d_z1n, d_s0, nullptr, g_bsk1, tb);
+        kg_rlwe_rows_kernel<F2, G2, 0, 3><<<(unsigned)(LWE2_N * 2 * G2::LEVELS), ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ck, KG_BSK2_A, KG_BSK2_E, d_z2n, d_s2, nullptr, g_bsk2, tb);
+        kg_rlwe_rows_kernel<F2, GT, 1, 3><<<(unsigned)(TR_STEPS * TR_LEVELS), ntt_kernel_threads<F2>(), ntt_kernel_smem<F2>(), s>>>(ck, KG_TRK_A, KG_TRK_E, d_z2n, nullptr, d_zs, g_trk, tb);
+        kg_ksk_rows_kernel<<<(unsigned)n_ksk_rows, KG_KSK_THREADS, 0, s>>>(ck, d_s2, d_z1, g_ksk);
+        ctx->launches += 11; CKC(cudaGetLastError());
+        if (gen->host_out) {
+            CKC(cudaMemcpyAsync((void*)gen->host_out->bsk1, g_bsk1, n_bsk1 * 4, cudaMemcpyDeviceToHost, s));
+            CKC(cudaMemcpyAsync((void*)gen->host_out->ksk, g_ksk, n_ksk_rows * LWE2_STRIDE_IN * 4, cudaMemcpyDeviceToHost, s));
+            CKC(cudaMemcpyAsync((void*)gen->host_out->bsk2, g_bsk2, n_bsk2 * 8, cudaMemcpyDeviceToHost, s));
+            CKC(cudaMemcpyAsync((void*)gen->host_out->trace, g_trk, n_trk * 8, cudaMemcpyDeviceToHost, s));
+        }
+        CKC(cudaStreamSynchronize(s));
+        gen_blobs = omr_key_blobs{g_bsk1, g_ksk, g_bsk2, g_trk, OMR_KEYS_NTT_NATIVE};
+        keys = &gen_blobs; keys_on_device = true;
+    }
+    const cudaMemcpyKind kind = keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     // device-resident keys were produced on some stream of the caller: the context's own (non-blocking) stream has no ordering
     // against it, so drain the device once before the first copy
     if (keys_on_device) CKC(cudaDeviceSynchronize());
@@ -473,6 +539,11 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
 
 extern "C" {
 
+int omr_generate_detector(int device, const omr_secret_key* sk, const uint8_t* seed32, const omr_key_blobs* host_keys_out, omr_ctx** out) {
+    if (host_keys_out && (!host_keys_out->bsk1 || !host_keys_out->ksk || !host_keys_out->bsk2 || !host_keys_out->trace)) { g_create_error = "generate_detector: null key buffer"; return OMR_ERR_INVALID; }
+    const KeygenSpec gen{sk, seed32, host_keys_out};
+    return create_impl(device, nullptr, false, out, &gen);
+}
 int omr_ctx_create(int device, const omr_key_blobs* keys, omr_ctx** out) { return create_impl(device, keys, false, out); }
 int omr_ctx_create_device_keys(int device, const omr_key_blobs* keys, omr_ctx** out) { return create_impl(device, keys, true, out); }
 
@@ -483,6 +554,8 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
                     ctx->ks_part, ctx->l2c_scratch, ctx->d_flag, ctx->ksg_bt, ctx->ksg_a, ctx->ksg_c, ctx->ksg_ws, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv, ctx->s_coeff};
     for (void* p : ptrs) if (p) cudaFree(p);
+    stream_release(ctx);
+    if (ctx->comm) { if (const NcclApi* api = nccl_api(nullptr)) api->comm_destroy(ctx->comm); ctx->comm = nullptr; }
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -761,6 +834,20 @@ int omr_pv_reset(omr_ctx* ctx) {
     return OMR_OK;
 }
 
+int omr_pv_load(omr_ctx* ctx, const uint64_t* pv, size_t count, uint64_t global_index0) {
+    if (!ctx || (count && !pv)) { ctx_fail(ctx, "pv_load: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
+    ctx->pv_count = 0; ctx->pv_any = false; ctx->pv_index0 = global_index0;
+    if (!count) return OMR_OK;
+    int st; if ((st = ensure_pv(ctx, count))) return st;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->pv, pv, count * OMR_PV_WORDS * sizeof(u64), cudaMemcpyHostToDevice, s));
+    if (ctx->out_domain == OMR_OUT_COEFF && (st = from_coeff_impl(ctx, ctx->pv, 2 * count, s))) return st;
+    CK(cudaStreamSynchronize(s));
+    ctx->pv_count = count; ctx->pv_any = true;
+    return OMR_OK;
+}
+
 int omr_detect_batch(omr_ctx* ctx, const uint16_t* clue_a, const uint16_t* clue_b, size_t B, uint64_t global_index0, uint64_t* pv_out,
                      omr_stage_times* times) {
     if (!ctx || (B && (!clue_a || !clue_b))) { ctx_fail(ctx, "detect: null argument"); return OMR_ERR_INVALID; }
@@ -963,6 +1050,142 @@ int omr_decode_digest(omr_ctx* ctx, const omr_retrieval_params* rp, const uint64
     }
     if (!solve_mod_257(m, pl, cc, cols)) { ctx_fail(ctx, "matrix is not invertible"); return OMR_ERR_INVALID; }   // error.rs:4-8
     for (size_t i = 0; i < cols * OMR_PAYLOAD_LEN; ++i) payloads_out[i] = (uint16_t)pl[i];
+    return OMR_OK;
+}
+
+// ---- streaming detection (README.md:9 "the detector processes incoming messages on-the-fly") -----------------------
+// A resident running digest: every push detects its messages and folds their index- and payload-digest contributions in,
+// stream-ordered on the context's stream.  Inputs go through two pinned staging buffers, so the host fills one while the copy
+// engine drains the other and there is no host synchronisation per chunk; omr_stream_snapshot is the only call that waits.
+// Packing is a sum over messages, so the running digest is bit-identical to packing the whole board at once.
+int omr_stream_begin(omr_ctx* ctx, const omr_retrieval_params* rp, uint64_t index_seed, const uint8_t* weight_seed32, uint64_t global_index0) {
+    if (!ctx || !rp || !weight_seed32) { ctx_fail(ctx, "stream_begin: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
+    int st; if ((st = check_rp(ctx, rp))) return st;
+    if (rp->cmb_count_per_cipher == 0 || rp->cmb_count_per_cipher * OMR_PAYLOAD_LEN > OMR_N2 || rp->combination_count == 0 ||
+        global_index0 > rp->all_payloads_count) { ctx_fail(ctx, "stream_begin: bad combination layout"); return OMR_ERR_INVALID; }
+    cudaStream_t s = ctx->stream;
+    CK(cudaStreamSynchronize(s));
+    stream_release(ctx);
+    auto& S = ctx->st;
+    S.rp = *rp; S.index_seed = index_seed; S.index0 = global_index0; S.count = 0;
+    S.n_idx = rp->max_encode_indices_cipher_count; S.n_pay = (rp->combination_count + rp->cmb_count_per_cipher - 1) / rp->cmb_count_per_cipher;
+    const size_t words = (size_t)(S.n_idx + S.n_pay) * OMR_PV_WORDS;
+    if ((st = dalloc(ctx, &S.digest, words)) || (st = dalloc(ctx, &S.part, words)) || (st = dalloc(ctx, &S.pv, STREAM_CHUNK * OMR_PV_WORDS))) { stream_release(ctx); return st; }
+    S.weight_elems = (size_t)S.n_pay * rp->cmb_count_per_cipher * rp->all_payloads_count;
+    if ((st = dalloc(ctx, &S.weights, S.weight_elems ? S.weight_elems : 1))) { stream_release(ctx); return st; }
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaMallocHost((void**)&S.pinned[i], STREAM_CHUNK * STREAM_MSG_BYTES);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&S.dev[i], STREAM_CHUNK * STREAM_MSG_BYTES);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.copied[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) { stream_release(ctx); ctx_fail(ctx, std::string("stream_begin: ") + cudaGetErrorString(e)); return OMR_ERR_ALLOC; }
+    }
+    CK(cudaMemsetAsync(S.digest, 0, words * sizeof(u64), s));
+    CK(cudaMemsetAsync(S.weights, 0, S.weight_elems * 2, s));                // rows beyond combination_count stay zero (detector.rs:370-371)
+    if ((st = weights_from_seed_impl(ctx, weight_seed32, (size_t)rp->combination_count * rp->all_payloads_count, S.weights, 0, s))) { stream_release(ctx); return st; }
+    CK(cudaStreamSynchronize(s));
+    S.active = true;
+    return OMR_OK;
+}
+
+int omr_stream_push(omr_ctx* ctx, const uint16_t* clue_a, const uint16_t* clue_b, const uint16_t* payloads, size_t n) {
+    if (!ctx || (n && (!clue_a || !clue_b || !payloads))) { ctx_fail(ctx, "stream_push: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
+    auto& S = ctx->st;
+    if (!S.active) { ctx_fail(ctx, "stream_push: no stream (call omr_stream_begin)"); return OMR_ERR_STATE; }
+    if (S.index0 + S.count + n > S.rp.all_payloads_count) { ctx_fail(ctx, "stream_push: more messages than all_payloads_count"); return OMR_ERR_INVALID; }
+    cudaStream_t s = ctx->stream;
+    int st;
+    if ((st = ensure_scratch(ctx, n < STREAM_CHUNK ? n : STREAM_CHUNK))) return st;
+    for (size_t off = 0; off < n; off += STREAM_CHUNK) {
+        const size_t nb = n - off < STREAM_CHUNK ? n - off : STREAM_CHUNK;
+        const int b = S.next; S.next ^= 1;
+        CK(cudaEventSynchronize(S.copied[b]));                               // the copy out of this pinned buffer two chunks ago is done
+        unsigned char* h = S.pinned[b];
+        const size_t na = nb * CLUE_N * 2, nbb = nb * CLUE_COUNT * 2, np = nb * PAYLOAD_LEN * 2;
+        memcpy(h, clue_a + off * CLUE_N, na); memcpy(h + na, clue_b + off * CLUE_COUNT, nbb); memcpy(h + na + nbb, payloads + off * PAYLOAD_LEN, np);
+        CK(cudaMemcpyAsync(S.dev[b], h, na + nbb + np, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(S.copied[b], s));
+        const unsigned short* d_a = reinterpret_cast<const unsigned short*>(S.dev[b]);
+        const unsigned short* d_b = reinterpret_cast<const unsigned short*>(S.dev[b] + na);
+        const unsigned short* d_p = reinterpret_cast<const unsigned short*>(S.dev[b] + na + nbb);
+        const u64 gi = S.index0 + S.count;
+        if ((st = detect_device(ctx, d_a, d_b, nb, S.pv, s, nullptr))) return st;
+        if ((st = encode_indices_impl(ctx, &S.rp, S.pv, nb, gi, S.index_seed, 0, S.n_idx, S.part, s))) return st;
+        if ((st = encode_payloads_impl(ctx, S.pv, d_p, nb, gi, S.weights, S.rp.all_payloads_count, S.n_pay, S.rp.cmb_count_per_cipher,
+                                       S.part + (size_t)S.n_idx * OMR_PV_WORDS, s))) return st;
+        const size_t words = (size_t)(S.n_idx + S.n_pay) * OMR_PV_WORDS;
+        digest_add_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(S.digest, S.part, words);
+        ++ctx->launches; CK(cudaGetLastError());
+        S.count += nb;
+    }
+    return OMR_OK;
+}
+
+int omr_stream_snapshot(omr_ctx* ctx, uint64_t* out, uint64_t* n_messages) {
+    if (!ctx || !out) { ctx_fail(ctx, "stream_snapshot: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
+    auto& S = ctx->st;
+    if (!S.active) { ctx_fail(ctx, "stream_snapshot: no stream (call omr_stream_begin)"); return OMR_ERR_STATE; }
+    int st; if ((st = copy_out_cts(ctx, out, S.digest, S.n_idx + S.n_pay, ctx->stream))) return st;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_messages) *n_messages = S.count;
+    return OMR_OK;
+}
+
+int omr_stream_end(omr_ctx* ctx) {
+    if (!ctx) return OMR_ERR_INVALID;
+    ENTER(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    stream_release(ctx);
+    return OMR_OK;
+}
+
+// ---- K7: cross-GPU sum of the partial digests (the rayon reduce + add_element_wise of detector.rs:333-336, 445-448) ---------------
+int omr_comm_unique_id(uint8_t* id128) {
+    std::string why;
+    const NcclApi* api = nccl_api(&why);
+    if (!id128 || !api) { omr::set_global_error(api ? "comm_unique_id: null argument" : why); return api ? OMR_ERR_INVALID : OMR_ERR_STATE; }
+    NcclUniqueId id;
+    const int rc = api->get_unique_id(&id);
+    if (rc) { omr::set_global_error(std::string("ncclGetUniqueId: ") + api->error_string(rc)); return OMR_ERR_CUDA; }
+    memcpy(id128, id.internal, sizeof id.internal);
+    return OMR_OK;
+}
+int omr_comm_init(omr_ctx* ctx, int n_ranks, int rank, const uint8_t* id128) {
+    if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) { ctx_fail(ctx, "comm_init: bad argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
+    std::string why;
+    const NcclApi* api = nccl_api(&why);
+    if (!api) { ctx_fail(ctx, why); return OMR_ERR_STATE; }
+    if (ctx->comm) { api->comm_destroy(ctx->comm); ctx->comm = nullptr; }
+    NcclUniqueId id; memcpy(id.internal, id128, sizeof id.internal);
+    const int rc = api->comm_init_rank(&ctx->comm, n_ranks, id, rank);
+    if (rc) { ctx->comm = nullptr; ctx_fail(ctx, std::string("ncclCommInitRank: ") + api->error_string(rc)); return OMR_ERR_CUDA; }
+    return OMR_OK;
+}
+int omr_comm_destroy(omr_ctx* ctx) {
+    if (!ctx) return OMR_ERR_INVALID;
+    ENTER(ctx);
+    if (ctx->comm) { if (const NcclApi* api = nccl_api(nullptr)) api->comm_destroy(ctx->comm); ctx->comm = nullptr; }
+    return OMR_OK;
+}
+// in place: d_digests [n_cipher][2][2048] canonical partial digests -> their sum over all ranks mod q2.  Values < q2 < 2^50, so a
+// raw u64 sum over up to 2^13 ranks cannot overflow; one small kernel reduces mod q2 right behind the collective on the stream.
+int omr_digest_allreduce(omr_ctx* ctx, void* nccl_comm, uint64_t* d_digests, size_t n_cipher, void* stream) {
+    if (!ctx || (n_cipher && !d_digests)) { ctx_fail(ctx, "digest_allreduce: null argument"); return OMR_ERR_INVALID; }
+    ENTER(ctx);
+    void* comm = nccl_comm ? nccl_comm : ctx->comm;
+    if (!comm) { ctx_fail(ctx, "digest_allreduce: no communicator (pass an ncclComm_t or call omr_comm_init)"); return OMR_ERR_STATE; }
+    std::string why;
+    const NcclApi* api = nccl_api(&why);
+    if (!api) { ctx_fail(ctx, why); return OMR_ERR_STATE; }
+    if (!n_cipher) return OMR_OK;
+    const size_t words = n_cipher * OMR_PV_WORDS;
+    const int rc = api->all_reduce(d_digests, d_digests, words, NcclApi::UINT64, NcclApi::SUM, comm, (cudaStream_t)stream);
+    if (rc) { ctx_fail(ctx, std::string("ncclAllReduce: ") + api->error_string(rc)); return OMR_ERR_CUDA; }
+    digest_mod_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>((u64*)d_digests, words);
+    ++ctx->launches; CK(cudaGetLastError());
     return OMR_OK;
 }
 

@@ -113,6 +113,50 @@ class Detector:
         if on_device:
             pass    # omr_ctx_create_device_keys drains the device before copying (the tensors may come from any torch stream)
 
+    @classmethod
+    def from_blob(cls, path, device=None):
+        """Detector::new from a detection-key blob on disk (omr_ctx_create_from_blob; the blob's domain selects the key flags)"""
+        torch = _torch()
+        self = cls.__new__(cls)
+        self.L = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        st = self.L.omr_ctx_create_from_blob(self.device, str(path).encode(), C.byref(h))
+        if st != _lib.OMR_OK:
+            raise OmrError(st, (self.L.omr_last_error(None) or b"").decode())
+        self.h = h
+        self.detection_key = None
+        return self
+
+    @classmethod
+    def generate(cls, secrets, seed, device=None, want_keys=False):
+        """SecretKeyPack::generate_detector (key_gen/secret.rs:118-187) with the key material made on the GPU
+        (omr_generate_detector).  secrets = (s0 [512] binary, z1 [1024] ternary, s2 [670] binary, z2 [2048] ternary) int32 arrays,
+        seed = 32 bytes from the caller's CSPRNG.  want_keys=True also returns the flat detection key as a DetectionKey of numpy
+        arrays (what the recipient ships to a detector)."""
+        torch = _torch()
+        self = cls.__new__(cls)
+        self.L = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        seed = bytes(seed)
+        if len(seed) != 32:
+            raise OmrError(_lib.OMR_ERR_INVALID, "the seed is 32 bytes")
+        arrs = [np.ascontiguousarray(x, np.int32) for x in secrets]
+        if [a.size for a in arrs] != [CLUE_N, N1, LWE2_N, N2]:
+            raise OmrError(_lib.OMR_ERR_INVALID, "secrets must be (s0[512], z1[1024], s2[670], z2[2048])")
+        sk = _lib.SecretKey(*[a.ctypes.data for a in arrs])
+        dk, blobs = None, None
+        if want_keys:
+            dk = DetectionKey(np.empty(BSK1_SHAPE, np.uint32), np.empty(KSK_SHAPE, np.uint32), np.empty(BSK2_SHAPE, np.uint64), np.empty(TRACE_SHAPE, np.uint64))
+            blobs = _lib.KeyBlobs(dk.bsk1.ctypes.data, dk.ksk.ctypes.data, dk.bsk2.ctypes.data, dk.trace.ctypes.data, _lib.KEYS_NTT_NATIVE)
+        h = C.c_void_p()
+        st = self.L.omr_generate_detector(self.device, C.byref(sk), seed, C.byref(blobs) if blobs is not None else None, C.byref(h))
+        if st != _lib.OMR_OK:
+            raise OmrError(st, (self.L.omr_last_error(None) or b"").decode())
+        self.h = h
+        self.detection_key = dk
+        return self
+
     def close(self):
         if getattr(self, "h", None):
             self.L.omr_ctx_destroy(self.h)
@@ -273,6 +317,57 @@ class Detector:
         self._ck(self.L.omr_digest_add_mod(self.h, running.data_ptr(), part.data_ptr(), running.numel(), self._stream()))
         return running
 
+    def digest_allreduce(self, digest, comm=None):
+        """K7 (omr_digest_allreduce): in-place sum over all ranks of the partial digests, mod q2, on the current stream.
+        comm = an ncclComm_t as an int (e.g. torch's ProcessGroupNCCL._comm_ptr()), or None for the communicator made by comm_init."""
+        n_cipher = digest.numel() // (2 * N2)
+        self._ck(self.L.omr_digest_allreduce(self.h, C.c_void_p(comm) if comm else None, digest.data_ptr(), n_cipher, self._stream()))
+        return digest
+
+    def comm_unique_id(self):
+        """rank 0: the 128-byte NCCL id to hand to every rank (omr_comm_unique_id)"""
+        buf = (C.c_uint8 * 128)()
+        st = self.L.omr_comm_unique_id(buf)
+        if st != _lib.OMR_OK:
+            raise OmrError(st, (self.L.omr_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        """every rank: join the library's own NCCL communicator (omr_comm_init)"""
+        if len(unique_id) != 128:
+            raise OmrError(_lib.OMR_ERR_INVALID, "the NCCL id is 128 bytes")
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.omr_comm_init(self.h, n_ranks, rank, buf))
+
+    def comm_destroy(self):
+        self._ck(self.L.omr_comm_destroy(self.h))
+
+    # -- streaming ingest (README.md:9; omr_stream_*) -----------------------------------------------------------------------
+    def stream_begin(self, retrieval_params, index_seed, weight_seed, global_index0=0):
+        weight_seed = bytes(weight_seed)
+        if len(weight_seed) != 32:
+            raise OmrError(_lib.OMR_ERR_INVALID, "the seed is 32 bytes")
+        rp = retrieval_params.to_c()
+        self._stream_cts = retrieval_params.max_encode_indices_cipher_count + retrieval_params.payload_cipher_count
+        self._ck(self.L.omr_stream_begin(self.h, C.byref(rp), index_seed, weight_seed, global_index0))
+
+    def stream_push(self, a, b, payloads):
+        """detect the next messages (host arrays) and fold them into the resident running digest; returns once the inputs are staged"""
+        a = np.ascontiguousarray(a, np.uint16).reshape(-1, CLUE_N); b = np.ascontiguousarray(b, np.uint16).reshape(-1, CLUE_COUNT)
+        payloads = np.ascontiguousarray(payloads, np.uint16).reshape(-1, PAYLOAD_LENGTH)
+        if not (a.shape[0] == b.shape[0] == payloads.shape[0]):
+            raise OmrError(_lib.OMR_ERR_INVALID, "Invalid clue count.")
+        self._ck(self.L.omr_stream_push(self.h, a.ctypes.data, b.ctypes.data, payloads.ctypes.data, a.shape[0]))
+
+    def stream_snapshot(self):
+        """(running digest [n_index + n_payload][2][2048] u64 in the output domain, messages folded in so far)"""
+        out = np.empty((self._stream_cts, 2, N2), np.uint64); n = C.c_uint64(0)
+        self._ck(self.L.omr_stream_snapshot(self.h, out.ctypes.data, C.byref(n)))
+        return out, int(n.value)
+
+    def stream_end(self):
+        self._ck(self.L.omr_stream_end(self.h))
+
     def decrypt_decode(self, z2_ntt, cts):
         """recipient side: decoded slots (values mod 257) of NTT-domain RLWE ciphertexts, int16 CUDA tensor [n][2048]"""
         torch = _torch()
@@ -303,6 +398,11 @@ class Detector:
     # -- host-buffer ("e2e") path: what the Rust shim binds ------------------------------------------------------------
     def pv_reset(self):
         self._ck(self.L.omr_pv_reset(self.h))
+
+    def pv_load(self, pv, global_index0=0):
+        """omr_pv_load: replace the resident store by host pertinency ciphertexts [count][2][2048] (output domain of the context)"""
+        pv = np.ascontiguousarray(pv, np.uint64).reshape(-1, 2, N2)
+        self._ck(self.L.omr_pv_load(self.h, pv.ctypes.data, pv.shape[0], global_index0))
 
     def detect_host(self, a, b, global_index0=0, want_pv=False):
         a = np.ascontiguousarray(a, np.uint16).reshape(-1, CLUE_N); b = np.ascontiguousarray(b, np.uint16).reshape(-1, CLUE_COUNT)
