@@ -19,19 +19,21 @@ FIELDS = {"L1": (134215681, 4073518), "L2": (1125899906826241, 765727830662934)}
 def _header_config(name):
     src = open(os.path.join(ROOT, "tfhe-omr_b200", "csrc", "ntt.cuh")).read()
     m = re.search(r"typedef GeoT<([^>]*)>\s+Geo%s;" % name, src)
-    v = [int(x) for x in m.group(1).split(",")]
+    toks = [x.strip() for x in m.group(1).split(",")]
+    blocked = toks[-1] == "true"
+    v = [int(x) for x in toks if x not in ("true", "false")]
     N, logn, NT, E, npass = v[:5]
     ns = v[5:5 + npass]
     pads = [(v[9 + 2 * x], v[10 + 2 * x]) for x in range(npass - 1)]
     assert N == 1 << logn and NT * E == N and sum(ns) == logn
-    return N, NT, E, ns, pads
+    return N, NT, E, ns, pads, blocked
 
 
 @pytest.mark.parametrize("name", ["L1", "L2"])
 def test_model_matches_header(name):
-    N, NT, E, ns, pads = _header_config(name)
+    N, NT, E, ns, pads, blocked = _header_config(name)
     cfg = LC.CONFIGS[name]
-    assert (cfg[0], cfg[1], cfg[2], cfg[3], cfg[5]) == (N, NT, E, ns, pads)
+    assert (cfg[0], cfg[1], cfg[2], cfg[3], cfg[5], cfg[6]) == (N, NT, E, ns, pads, blocked)
 
 
 @pytest.mark.parametrize("name", ["L1", "L2"])
@@ -66,7 +68,7 @@ def test_register_schedule_matches_reference_ntt(name):
         stride = (N >> s0) // EP
         for tt in range(NT):
             for g in range(E // EP):
-                j = (tt + NT * g) // stride
+                j = LC.vthread(cfg, p, tt, g) // stride
                 pos = [LC.idx(cfg, p, tt, g * EP + kk) for kk in range(EP)]
                 for l in range(ns[p]):
                     half = EP >> (l + 1)
@@ -77,3 +79,20 @@ def test_register_schedule_matches_reference_ntt(name):
                             u, v = x[lo], x[hi] * w % q
                             x[lo], x[hi] = (u + v) % q, (u - v) % q
     assert x == ref
+
+
+def test_no_exchange_hazards_under_arbitrary_warp_interleavings():
+    """the warp-blocked level-2 geometry replaces two of three exchange barriers by __syncwarp(): replay the store/sync/load
+    sequences of the kernels under random warp schedules and require every load to see its own store (scripts/layout_check.py)"""
+    progs = {"K3 step": ["F2"] * 6 + ["I2", "B"] + ["F2"] * 2 + ["I2", "B"], "K4 step + final": ["F2"] * 3 + ["I2", "B", "B", "F2"],
+             "pack": ["F"] * 4, "cluster": ["F2", "I", "B", "F2", "I", "B"], "ntt_kernel": ["I", "F"], "mixed": ["F", "I", "F2", "I2", "F", "I"]}
+    for name, prog in progs.items():
+        assert LC.race_check("L2", prog, schedules=25) is None, name
+    assert LC.race_check("L1", ["F", "I", "I2", "F"], schedules=5) is None
+    # the detector itself: the unpadded first exchange lets warp w's private region overlap warp w+1's and must be flagged
+    saved = LC.CONFIGS["L2"]
+    try:
+        LC.CONFIGS["L2"] = saved[:5] + ([(0, 0)] + saved[5][1:],) + saved[6:]
+        assert LC.race_check("L2", ["F2", "I2", "B"], schedules=25) is not None
+    finally:
+        LC.CONFIGS["L2"] = saved

@@ -160,7 +160,7 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
     unsigned short* ca = ca_all + slot * CLUE_N;
     ExBuf<u32> eb{acc + 2 * N, acc + 2 * N + GEO::BUF};
     if (threadIdx.x == 0) mbar_init(mbar, 1);
-    for (int i = threadIdx.x; i < N; i += THREADS) { s_tw[i] = tb.tw1[i]; s_itw_smem[i] = tb.itw1[i]; }
+    fill_twiddles_deint<GEO>(s_tw, tb.tw1, threadIdx.x, THREADS); fill_twiddles_deint<GEO>(s_itw_smem, tb.itw1, threadIdx.x, THREADS);
     for (int i = t; i < CLUE_N; i += L1_GROUP) ca[i] = clue_a[(size_t)msg * CLUE_N + i] & (CLUE_Q - 1);   // canonical mod 2048
     init_acc<F, GEO>(acc, tb.lut1, clue_b[(size_t)msg * CLUE_COUNT + c] & (CLUE_Q - 1), t);
     __syncthreads();
@@ -184,7 +184,7 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
                 u32 x[E];
 #pragma unroll
                 for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, G>(u[k], r);
-                ntt_forward<AR, GEO, LdSharedC>(x, eb, s_tw, t, bar);
+                ntt_forward<AR, GEO, LdSharedD>(x, eb, s_tw, t, bar);
                 if (r == 0 && p == 0) { mbar_wait(mbar, phase & 1); ++phase; }             // tile i has landed
                 const u32* ka = ktile + (size_t)(p * L + r) * 2 * N + out_idx<GEO>(t, 0);
                 const u32* kb = ka + N;
@@ -203,7 +203,7 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
         __syncthreads();                                                         // every group is done with tile i
         if (threadIdx.x == 0 && i + 1 < CLUE_N) tma_load(ktile, bsk1 + (size_t)(i + 1) * L1_TILE_WORDS, CFG::TILE_WORDS * 4, mbar);
         // both inverse transforms in flight (two buffers, staggered exchanges): twice the ILP of running them back to back
-        ntt_inverse2s<AR, GEO, LdShared>(ya, yb, eb.a, eb.b, s_itw_smem, t, bar);
+        ntt_inverse2s<AR, GEO, LdSharedDI>(ya, yb, eb.a, eb.b, s_itw_smem, t, bar);
 #pragma unroll
         for (int k = 0; k < E; ++k) {
             const int pos = t + GEO::NT * k;
@@ -248,7 +248,7 @@ l1_blind_rotate_lat_kernel(const unsigned short* __restrict__ clue_a, const unsi
     const int p = g / L, r = g % L;
     u32* mine = bufs + (size_t)g * 2 * GEO::BUF;
     if (threadIdx.x == 0) mbar_init(mbar, 1);
-    for (int i = threadIdx.x; i < N; i += L1L_THREADS) { s_tw[i] = tb.tw1[i]; s_itw[i] = tb.itw1[i]; }
+    fill_twiddles_deint<GEO>(s_tw, tb.tw1, threadIdx.x, L1L_THREADS); fill_twiddles_deint<GEO>(s_itw, tb.itw1, threadIdx.x, L1L_THREADS);
     for (int i = threadIdx.x; i < CLUE_N; i += L1L_THREADS) ca[i] = clue_a[(size_t)msg * CLUE_N + i] & (CLUE_Q - 1);
     if (g == 0) init_acc<F, GEO>(acc, tb.lut1, clue_b[(size_t)msg * CLUE_COUNT + c] & (CLUE_Q - 1), t);
     __syncthreads();
@@ -262,7 +262,7 @@ l1_blind_rotate_lat_kernel(const unsigned short* __restrict__ clue_a, const unsi
 #pragma unroll
         for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, G>(u[k], r);
         ExBuf<u32> eb{mine, mine + GEO::BUF};
-        ntt_forward<AR, GEO, LdSharedC>(x, eb, s_tw, t, bar);
+        ntt_forward<AR, GEO, LdSharedD>(x, eb, s_tw, t, bar);
         mbar_wait(mbar, i & 1);                                                  // tile i has landed
         const u32* ka = ktile + (size_t)g * 2 * N + out_idx<GEO>(t, 0);
         const u32* kb = ka + N;
@@ -292,7 +292,7 @@ l1_blind_rotate_lat_kernel(const unsigned short* __restrict__ clue_a, const unsi
 #pragma unroll
             for (int k = 0; k < E; ++k) y[k] = tot[g * N + t + GEO::NT * k];
             ExBuf<u32> ei{mine, mine + GEO::BUF};
-            ntt_inverse<AR, GEO, LdShared>(y, ei, s_itw, t, bar);
+            ntt_inverse<AR, GEO, LdSharedDI>(y, ei, s_itw, t, bar);
 #pragma unroll
             for (int k = 0; k < E; ++k) {
                 const int pos = g * N + t + GEO::NT * k;
@@ -339,7 +339,7 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
     double2* s_tw = reinterpret_cast<double2*>(by + GEO::BUF);          // forward twiddles: the L1 cache left beside 2 x 100 KiB
     unsigned short* la = reinterpret_cast<unsigned short*>(s_tw + N);   // of shared memory is too small to hold them
     const int msg = blockIdx.x, t = threadIdx.x;
-    for (int i = t; i < N; i += L2_THREADS) s_tw[i] = tb.tw2d[i];
+    fill_twiddles_deint<GEO>(s_tw, tb.tw2d, t, L2_THREADS);
     for (int i = t; i < LWE2_STRIDE_IN; i += L2_THREADS) la[i] = (unsigned short)(lwe[(size_t)msg * LWE2_STRIDE_IN + i] & (LWE2_Q - 1));
     __syncthreads();
     init_acc<F, GEO>(acc, tb.lut2, la[LWE2_N], t);
@@ -364,7 +364,7 @@ l2_blind_rotate_kernel(const u32* __restrict__ lwe, const double* __restrict__ b
                     x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r));
                     y[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r + 1));
                 }
-                ntt_forward2s<AR, GEO, LdSharedC>(x, y, bx, by, s_tw, t, 0);
+                ntt_forward2s<AR, GEO, LdSharedD>(x, y, bx, by, s_tw, t, 0);
                 const double* kx = key + (size_t)(p * L + r) * 2 * N;         // rows r and r+1: [a | b] each
 #pragma unroll
                 for (int k = 0; k < E; k += 2) {
@@ -414,7 +414,7 @@ l2_blind_rotate_lat_kernel(const u32* __restrict__ lwe, const double* __restrict
     unsigned short* la = reinterpret_cast<unsigned short*>(s_tw + N);
     const int msg = blockIdx.x, h = threadIdx.x / GEO::NT, t = threadIdx.x % GEO::NT, bar = 1 + h;
     double* bx = bufs + (size_t)h * 2 * GEO::BUF; double* by = bx + GEO::BUF;
-    for (int i = threadIdx.x; i < N; i += L2L_THREADS) s_tw[i] = tb.tw2d[i];
+    fill_twiddles_deint<GEO>(s_tw, tb.tw2d, threadIdx.x, L2L_THREADS);
     for (int i = threadIdx.x; i < LWE2_STRIDE_IN; i += L2L_THREADS) la[i] = (unsigned short)(lwe[(size_t)msg * LWE2_STRIDE_IN + i] & (LWE2_Q - 1));
     __syncthreads();
     if (h == 0) init_acc<F, GEO>(acc, tb.lut2, la[LWE2_N], t);
@@ -437,7 +437,7 @@ l2_blind_rotate_lat_kernel(const u32* __restrict__ lwe, const double* __restrict
                 x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r));
                 y[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r + 1));
             }
-            ntt_forward2s<AR, GEO, LdSharedC>(x, y, bx, by, s_tw, t, bar);
+            ntt_forward2s<AR, GEO, LdSharedD>(x, y, bx, by, s_tw, t, bar);
             const double* kx = key + (size_t)r * 2 * N;
 #pragma unroll
             for (int k = 0; k < E; k += 2) {
@@ -497,7 +497,7 @@ l2_blind_rotate_cluster_kernel(const u32* __restrict__ lwe, const double* __rest
     const int msg = blockIdx.x / L2C_CLUSTER, c = blockIdx.x % L2C_CLUSTER, t = threadIdx.x;
     const int p = c / 3, r0 = 2 * (c % 3);
     double* scr = scratch + (size_t)msg * L2C_SCRATCH_WORDS;
-    for (int i = t; i < N; i += GEO::NT) s_tw[i] = tb.tw2d[i];
+    fill_twiddles_deint<GEO>(s_tw, tb.tw2d, t, GEO::NT);
     for (int i = t; i < LWE2_STRIDE_IN; i += GEO::NT) la[i] = (unsigned short)(lwe[(size_t)msg * LWE2_STRIDE_IN + i] & (LWE2_Q - 1));
     __syncthreads();
     {
@@ -524,7 +524,7 @@ l2_blind_rotate_cluster_kernel(const u32* __restrict__ lwe, const double* __rest
             x[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r0));
             y[k] = D2::from_small(gadget_digit_signed<F, G>(u[k], r0 + 1));
         }
-        ntt_forward2s<AR, GEO, LdSharedC>(x, y, bx, by, s_tw, t, 0);
+        ntt_forward2s<AR, GEO, LdSharedD>(x, y, bx, by, s_tw, t, 0);
 #pragma unroll
         for (int k = 0; k < E; k += 2) {
             const int o = out_idx<GEO>(0, k) - out_idx<GEO>(0, 0);

@@ -14,9 +14,14 @@
 
 namespace omr {
 
-template <int N_, int LOGN_, int NT_, int E_, int NP_, int NS0, int NS1, int NS2, int NS3, int A0, int S0_, int A1, int S1_, int A2, int S2_>
+template <int N_, int LOGN_, int NT_, int E_, int NP_, int NS0, int NS1, int NS2, int NS3, int A0, int S0_, int A1, int S1_, int A2, int S2_, bool WARP_BLOCKED_ = false>
 struct GeoT {
     static constexpr int N = N_, LOGN = LOGN_, NT = NT_, E = E_, NPASS = NP_;
+    // WARP_BLOCKED: every pass after the first keeps warp w inside coefficients [w * 32 * E, (w + 1) * 32 * E) — the last pass takes
+    // its register groups from consecutive 32-thread slices of the warp's own block instead of from NT-strided ones — so all
+    // exchanges but the first are private to a warp and need __syncwarp() instead of a barrier over the whole group.
+    static constexpr bool WARP_BLOCKED = WARP_BLOCKED_;
+    __host__ __device__ static constexpr bool warp_local(int x) { return WARP_BLOCKED && x >= 1; }
     __host__ __device__ static constexpr int ns(int p) { return p == 0 ? NS0 : p == 1 ? NS1 : p == 2 ? NS2 : NS3; }
     __host__ __device__ static constexpr int s0(int p) { return p == 0 ? 0 : p == 1 ? NS0 : p == 2 ? NS0 + NS1 : NS0 + NS1 + NS2; }
     __host__ __device__ static constexpr int pad_a(int x) { return x == 0 ? A0 : x == 1 ? A1 : A2; }
@@ -27,17 +32,20 @@ struct GeoT {
     static constexpr int BUF = (cmax(cmax(phys(0, N - 1), phys(1, N - 1)), NP_ > 3 ? phys(2, N - 1) : 0) + 1 + 3) & ~3;
 };
 typedef GeoT<1024, 10, 64, 16, 3, 4, 4, 2, 0, 4, 6, 4, 6, 0, 0> GeoL1;     // 4-byte elements
-typedef GeoT<2048, 11, 256, 8, 4, 3, 3, 3, 2, 0, 0, 4, 5, 2, 4> GeoL2;     // 8-byte elements
+typedef GeoT<2048, 11, 256, 8, 4, 3, 3, 3, 2, 32, 8, 4, 5, 2, 4, true> GeoL2;   // 8-byte elements; every exchange keeps warp w in [288 w, 288 w + 288)
 
 // Pass P of geometry GEO: element k (0..E-1) of thread t:  group g = k / EP, kk = k % EP, vt = t + NT*g,
 //   blk = N >> S0, stride = blk / EP, j = vt / stride, i = vt % stride, idx = j*blk + i + kk*stride.
 template <class GEO, int P> struct Pass {
     static constexpr int S0 = GEO::s0(P), NS = GEO::ns(P), EP = 1 << NS, G = GEO::E / EP;
     static constexpr int BLK = GEO::N >> S0, STRIDE = BLK / EP;
+    static constexpr bool BLOCKED = GEO::WARP_BLOCKED && P == GEO::NPASS - 1;
+    // virtual thread of register group g: NT-strided, or (warp-blocked last pass) the g-th 32-thread slice of the warp's block
+    __host__ __device__ static constexpr int vt(int t, int g) { return BLOCKED ? (t / 32) * 32 * G + (t % 32) + 32 * g : t + GEO::NT * g; }
     __host__ __device__ static constexpr int idx(int t, int k) {
-        return ((t + GEO::NT * (k / EP)) / STRIDE) * BLK + ((t + GEO::NT * (k / EP)) % STRIDE) + (k % EP) * STRIDE;
+        return (vt(t, k / EP) / STRIDE) * BLK + (vt(t, k / EP) % STRIDE) + (k % EP) * STRIDE;
     }
-    static __device__ __forceinline__ int block_of(int t, int g) { return (t + GEO::NT * g) / STRIDE; }
+    static __device__ __forceinline__ int block_of(int t, int g) { return vt(t, g) / STRIDE; }
     // physical offset of element k relative to element 0 in exchange X (thread independent, checked by layout_check.py)
     template <int X> __host__ __device__ static constexpr int off(int k) { return GEO::phys(X, idx(0, k)) - GEO::phys(X, idx(0, 0)); }
     template <int X> static __device__ __forceinline__ int base(int t) { return GEO::phys(X, idx(t, 0)); }
@@ -142,9 +150,33 @@ template <class TW> struct HasConstHead { static constexpr bool value = false; }
 template <> struct HasConstHead<uint2> { static constexpr bool value = true; };
 template <> struct HasConstHead<double2> { static constexpr bool value = true; };
 
-struct LdGlobal { static constexpr bool USE_CONST_HEAD = false; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return __ldg(p); } };
-struct LdShared { static constexpr bool USE_CONST_HEAD = false; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
-struct LdSharedC { static constexpr bool USE_CONST_HEAD = true; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
+struct LdGlobal { static constexpr bool USE_CONST_HEAD = false, DEINT = false; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return __ldg(p); } };
+struct LdShared { static constexpr bool USE_CONST_HEAD = false, DEINT = false; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
+struct LdSharedC { static constexpr bool USE_CONST_HEAD = true, DEINT = false; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
+// Shared-memory tables in DE-INTERLEAVED order (filled by fill_twiddles_deint): the twiddle of stage S0 + l of the pass that
+// starts at stage S0, block j, sub-butterfly sb sits at 2^(S0+l) + sb 2^S0 + j instead of 2^(S0+l) + (j << l) + sb.  In the last
+// pass every lane has its own j, so the interleaved order makes lanes read at twice (l = 1) the vector stride — a 2-way bank
+// conflict on every such load; de-interleaved, consecutive lanes read consecutive words.  D = forward (+ constant head), DI = inverse.
+struct LdSharedD { static constexpr bool USE_CONST_HEAD = true, DEINT = true; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
+struct LdSharedDI { static constexpr bool USE_CONST_HEAD = false, DEINT = true; template <class TW> static __device__ __forceinline__ TW ld(const TW* p) { return *p; } };
+template <class LD> __device__ __forceinline__ constexpr int tw_index(int s0, int l, int j, int sb) {
+    return LD::DEINT ? (1 << (s0 + l)) + (sb << s0) + j : (1 << (s0 + l)) + (j << l) + sb;
+}
+// copy a bit-reversed twiddle table (global, interleaved) into shared memory in de-interleaved order
+template <class GEO, class TW> __device__ __forceinline__ void fill_twiddles_deint(TW* __restrict__ dst, const TW* __restrict__ src, int tid, int nthreads) {
+    for (int i = tid; i < GEO::N; i += nthreads) {
+        int o = i;
+        if (i > 0) {
+            const int s = 31 - __clz(i);                                    // stage
+            int p = 0;
+#pragma unroll
+            for (int q = 1; q < GEO::NPASS; ++q) if (s >= GEO::s0(q)) p = q;
+            const int s0 = GEO::s0(p), l = s - s0, r = i - (1 << s);
+            o = (1 << s) + ((r & ((1 << l) - 1)) << s0) + (r >> l);
+        }
+        dst[o] = src[i];
+    }
+}
 
 template <class AR, class GEO, int P, class LD>
 __device__ __forceinline__ void fwd_pass(typename AR::T (&x)[GEO::E], const typename AR::TW* __restrict__ tw, int t) {
@@ -160,7 +192,7 @@ __device__ __forceinline__ void fwd_pass(typename AR::T (&x)[GEO::E], const type
             for (int sb = 0; sb < (1 << l); ++sb) {
                 typename AR::TW w;
                 if constexpr (P == 0 && HasConstHead<typename AR::TW>::value && LD::USE_CONST_HEAD) w = const_head<typename AR::TW>()[(1 << l) + sb];
-                else w = LD::ld(&tw[(1 << (PS::S0 + l)) + (j << l) + sb]);
+                else w = LD::ld(&tw[tw_index<LD>(PS::S0, l, j, sb)]);
 #pragma unroll
                 for (int h = 0; h < half; ++h) {
                     const int lo = g * PS::EP + sb * 2 * half + h, hi = lo + half;
@@ -185,7 +217,7 @@ __device__ __forceinline__ void inv_pass(typename AR::T (&x)[GEO::E], const type
             const int half = PS::EP >> (l + 1);
 #pragma unroll
             for (int sb = 0; sb < (1 << l); ++sb) {
-                const typename AR::TW w = LD::ld(&itw[(1 << (PS::S0 + l)) + (j << l) + sb]);
+                const typename AR::TW w = LD::ld(&itw[tw_index<LD>(PS::S0, l, j, sb)]);
 #pragma unroll
                 for (int h = 0; h < half; ++h) {
                     const int lo = g * PS::EP + sb * 2 * half + h, hi = lo + half;
@@ -205,6 +237,17 @@ template <int NTHREADS> __device__ __forceinline__ void group_sync(int bar_id) {
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NTHREADS) : "memory");
 }
 
+// barrier of exchange X: private to the warp when the geometry keeps it inside one warp's block
+template <class GEO, int X> __device__ __forceinline__ void exchange_sync(int bar_id) {
+    if constexpr (GEO::warp_local(X)) __syncwarp(); else group_sync<GEO::NT>(bar_id);
+}
+// With warp-private exchanges the warps of a group drift apart between group barriers, and the FIRST exchange of a forward
+// transform stores into every warp's region: a group barrier in front of that store keeps it behind the last private exchange of
+// the slowest warp.  (The first exchange of an inverse transform stores into the warp's own region and needs none.)
+template <class GEO> __device__ __forceinline__ void pre_first_exchange(int bar_id) {
+    if constexpr (GEO::WARP_BLOCKED) group_sync<GEO::NT>(bar_id);
+}
+
 // two exchange buffers used alternately by EVERY exchange of the group (forward, inverse, any polynomial): a write to
 // one buffer is always separated from the last read of it by the barrier of the exchange in between.
 template <class T> struct ExBuf {
@@ -217,12 +260,13 @@ template <class AR, class GEO, class LD>
 __device__ __forceinline__ void ntt_forward(typename AR::T (&x)[GEO::E], ExBuf<typename AR::T>& eb, const typename AR::TW* __restrict__ tw, int t, int bar) {
     typedef typename AR::T T;
     fwd_pass<AR, GEO, 0, LD>(x, tw, t);
-    { T* w = eb.next(); ex_store<GEO, 0, 0>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 1, 0>(x, w, t); }
+    pre_first_exchange<GEO>(bar);
+    { T* w = eb.next(); ex_store<GEO, 0, 0>(x, w, t); exchange_sync<GEO, 0>(bar); ex_load<GEO, 1, 0>(x, w, t); }
     fwd_pass<AR, GEO, 1, LD>(x, tw, t);
-    { T* w = eb.next(); ex_store<GEO, 1, 1>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 2, 1>(x, w, t); }
+    { T* w = eb.next(); ex_store<GEO, 1, 1>(x, w, t); exchange_sync<GEO, 1>(bar); ex_load<GEO, 2, 1>(x, w, t); }
     fwd_pass<AR, GEO, 2, LD>(x, tw, t);
     if constexpr (GEO::NPASS == 4) {
-        { T* w = eb.next(); ex_store<GEO, 2, 2>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 3, 2>(x, w, t); }
+        { T* w = eb.next(); ex_store<GEO, 2, 2>(x, w, t); exchange_sync<GEO, 2>(bar); ex_load<GEO, 3, 2>(x, w, t); }
         fwd_pass<AR, GEO, 3, LD>(x, tw, t);
     }
 }
@@ -232,12 +276,12 @@ __device__ __forceinline__ void ntt_inverse(typename AR::T (&x)[GEO::E], ExBuf<t
     typedef typename AR::T T;
     if constexpr (GEO::NPASS == 4) {
         inv_pass<AR, GEO, 3, LD>(x, itw, t);
-        { T* w = eb.next(); ex_store<GEO, 3, 2>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 2, 2>(x, w, t); }
+        { T* w = eb.next(); ex_store<GEO, 3, 2>(x, w, t); exchange_sync<GEO, 2>(bar); ex_load<GEO, 2, 2>(x, w, t); }
     }
     inv_pass<AR, GEO, 2, LD>(x, itw, t);
-    { T* w = eb.next(); ex_store<GEO, 2, 1>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 1, 1>(x, w, t); }
+    { T* w = eb.next(); ex_store<GEO, 2, 1>(x, w, t); exchange_sync<GEO, 1>(bar); ex_load<GEO, 1, 1>(x, w, t); }
     inv_pass<AR, GEO, 1, LD>(x, itw, t);
-    { T* w = eb.next(); ex_store<GEO, 1, 0>(x, w, t); group_sync<GEO::NT>(bar); ex_load<GEO, 0, 0>(x, w, t); }
+    { T* w = eb.next(); ex_store<GEO, 1, 0>(x, w, t); exchange_sync<GEO, 0>(bar); ex_load<GEO, 0, 0>(x, w, t); }
     inv_pass<AR, GEO, 0, LD>(x, itw, t);
 }
 
@@ -245,20 +289,21 @@ __device__ __forceinline__ void ntt_inverse(typename AR::T (&x)[GEO::E], ExBuf<t
 // buffer is separated from the previous loads of it by a barrier: store x | bar | load x, store y | bar | load y.
 template <class AR, class GEO, int P, int X, class T>
 __device__ __forceinline__ void exchange2s(T (&x)[GEO::E], T (&y)[GEO::E], T* bx, T* by, int t, int bar) {
-    ex_store<GEO, P, X>(x, bx, t); group_sync<GEO::NT>(bar);
-    ex_load<GEO, P + 1, X>(x, bx, t); ex_store<GEO, P, X>(y, by, t); group_sync<GEO::NT>(bar);
+    ex_store<GEO, P, X>(x, bx, t); exchange_sync<GEO, X>(bar);
+    ex_load<GEO, P + 1, X>(x, bx, t); ex_store<GEO, P, X>(y, by, t); exchange_sync<GEO, X>(bar);
     ex_load<GEO, P + 1, X>(y, by, t);
 }
 template <class AR, class GEO, int P, int X, class T>
 __device__ __forceinline__ void exchange2s_inv(T (&x)[GEO::E], T (&y)[GEO::E], T* bx, T* by, int t, int bar) {
-    ex_store<GEO, P + 1, X>(x, bx, t); group_sync<GEO::NT>(bar);
-    ex_load<GEO, P, X>(x, bx, t); ex_store<GEO, P + 1, X>(y, by, t); group_sync<GEO::NT>(bar);
+    ex_store<GEO, P + 1, X>(x, bx, t); exchange_sync<GEO, X>(bar);
+    ex_load<GEO, P, X>(x, bx, t); ex_store<GEO, P + 1, X>(y, by, t); exchange_sync<GEO, X>(bar);
     ex_load<GEO, P, X>(y, by, t);
 }
 template <class AR, class GEO, class LD>
 __device__ __forceinline__ void ntt_forward2s(typename AR::T (&x)[GEO::E], typename AR::T (&y)[GEO::E], typename AR::T* bx, typename AR::T* by,
                                               const typename AR::TW* __restrict__ tw, int t, int bar) {
     fwd_pass<AR, GEO, 0, LD>(x, tw, t); fwd_pass<AR, GEO, 0, LD>(y, tw, t);
+    pre_first_exchange<GEO>(bar);
     exchange2s<AR, GEO, 0, 0>(x, y, bx, by, t, bar);
     fwd_pass<AR, GEO, 1, LD>(x, tw, t); fwd_pass<AR, GEO, 1, LD>(y, tw, t);
     exchange2s<AR, GEO, 1, 1>(x, y, bx, by, t, bar);
