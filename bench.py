@@ -182,24 +182,23 @@ def multi_gpu_check(omr, torch, dist, np, rank, world, local, dev):
     gathered = [torch.empty_like(part) for _ in range(world)]
     dist.all_gather(gathered, part)
     via_torch = part.clone(); dist.all_reduce(via_torch); det.digest_reduce_mod(via_torch)
-    via_lib = part.clone()
-    comm = None
+    libs = []                                              # (path description, reduced digest) through omr_digest_allreduce
     try:
         comm = dist.distributed_c10d._get_default_group()._get_backend(torch.device(dev))._comm_ptr()
     except Exception:
         comm = None
     if comm:
-        det.digest_allreduce(via_lib, comm=comm)
-        lib_path = "omr_digest_allreduce on torch's ncclComm_t"
-    else:                                                  # the library's own communicator: rank 0 draws the id, torch broadcasts it
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid.copy_(torch.tensor(list(det.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        det.comm_init(world, rank, bytes(uid.cpu().tolist()))
-        det.digest_allreduce(via_lib)
-        det.comm_destroy()
-        lib_path = "omr_digest_allreduce on the library's own communicator (omr_comm_init)"
+        t = part.clone(); det.digest_allreduce(t, comm=comm); libs.append(("omr_digest_allreduce on torch's ncclComm_t", t))
+    # ... and on the library's own communicator: rank 0 draws the id, torch broadcasts it (a non-Python caller uses its own channel)
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.tensor(list(det.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    det.comm_init(world, rank, bytes(uid.cpu().tolist()))
+    t = part.clone(); det.digest_allreduce(t); libs.append(("omr_digest_allreduce on the library's own communicator (omr_comm_unique_id / omr_comm_init)", t))
+    torch.cuda.synchronize()
+    det.comm_destroy()
+    via_lib = libs[-1][1]
     torch.cuda.synchronize()
     ok, why = True, ""
     if rank == 0:
@@ -209,8 +208,9 @@ def multi_gpu_check(omr, torch, dist, np, rank, world, local, dev):
         want = np.array([int(v) % Q2 for v in want], dtype=np.uint64).reshape(part.shape)
         if not np.array_equal(via_torch.cpu().numpy().view(np.uint64), want):
             ok, why = False, "all_reduce + reduce_mod differs from the integer sum"
-        if ok and not np.array_equal(via_lib.cpu().numpy().view(np.uint64), want):
-            ok, why = False, "omr_digest_allreduce differs from the integer sum"
+        for desc, t in libs:
+            if ok and not np.array_equal(t.cpu().numpy().view(np.uint64), want):
+                ok, why = False, f"{desc} differs from the integer sum"
         if ok:
             z2 = secrets[3].astype(np.int64)
             z2c = np.where(z2 < 0, Q2 + z2, z2).astype(np.uint64)
@@ -227,7 +227,7 @@ def multi_gpu_check(omr, torch, dist, np, rank, world, local, dev):
                 ok, why = False, f"decode failed: {e}"
     det.close()
     flag = torch.tensor([1 if ok else 0], device=dev); dist.broadcast(flag, 0)
-    return {"result": "ok" if int(flag.item()) else f"FAILED: {why}", "messages": D, "planted": planted, "collective_paths": ["torch all_reduce + omr_digest_reduce_mod", lib_path]}
+    return {"result": "ok" if int(flag.item()) else f"FAILED: {why}", "messages": D, "planted": planted, "collective_paths": ["torch all_reduce + omr_digest_reduce_mod"] + [d for d, _ in libs]}
 
 
 def run_ours(args):

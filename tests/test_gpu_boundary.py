@@ -151,10 +151,10 @@ def test_calls_restore_the_current_device(detector, small):
 
 
 def test_stream_push_equals_one_shot(detector, keypack, decoy):
-    """an ingest loop with arbitrary push sizes (crossing the 4 096-message staging chunk) builds the same
+    """an ingest loop with arbitrary push sizes (crossing the 16 384-message staging chunk) builds the same
     resident digest, word for word, as detect + encode over the same messages in one shot — and it decodes."""
     import tfhe_omr_b200 as omr
-    n, D, index0 = 4300, 6000, 1000
+    n, D, index0 = 16500, 20000, 1000
     rng = np.random.default_rng(8)
     a, b = decoy.gen_clues(41, n, threads=16)
     planted = np.sort(rng.choice(n, 5, replace=False))
@@ -172,7 +172,7 @@ def test_stream_push_equals_one_shot(detector, keypack, decoy):
     got0, n0 = detector.stream_snapshot()
     assert n0 == 0 and not got0.any()
     lo = 0
-    for sz in (1, 0, 7, 4097, 2, 193):
+    for sz in (1, 0, 7, 16385, 2, 105):
         detector.stream_push(a[lo:lo + sz], b[lo:lo + sz], payloads[lo:lo + sz]); lo += sz
     assert lo == n
     got, cnt = detector.stream_snapshot()

@@ -94,7 +94,7 @@ struct omr_ctx {
         int next = 0;
     } st;
 };
-constexpr size_t STREAM_CHUNK = 4096;                                        // messages per staged chunk
+constexpr size_t STREAM_CHUNK = 16384;                                       // messages per staged chunk (= the detect chunk: whole waves of both big kernels)
 constexpr size_t STREAM_MSG_BYTES = (CLUE_N + CLUE_COUNT + PAYLOAD_LEN) * 2; // clue a, clue b, payload
 
 namespace omr {            // ks_gemm.cu: the key switch as an int8 tensor-core GEMM (a CUTLASS template instance; opt-in), if it was compiled in
@@ -1066,20 +1066,25 @@ int omr_stream_begin(omr_ctx* ctx, const omr_retrieval_params* rp, uint64_t inde
         global_index0 > rp->all_payloads_count) { ctx_fail(ctx, "stream_begin: bad combination layout"); return OMR_ERR_INVALID; }
     cudaStream_t s = ctx->stream;
     CK(cudaStreamSynchronize(s));
-    stream_release(ctx);
     auto& S = ctx->st;
-    S.rp = *rp; S.index_seed = index_seed; S.index0 = global_index0; S.count = 0;
-    S.n_idx = rp->max_encode_indices_cipher_count; S.n_pay = (rp->combination_count + rp->cmb_count_per_cipher - 1) / rp->cmb_count_per_cipher;
-    const size_t words = (size_t)(S.n_idx + S.n_pay) * OMR_PV_WORDS;
-    if ((st = dalloc(ctx, &S.digest, words)) || (st = dalloc(ctx, &S.part, words)) || (st = dalloc(ctx, &S.pv, STREAM_CHUNK * OMR_PV_WORDS))) { stream_release(ctx); return st; }
-    S.weight_elems = (size_t)S.n_pay * rp->cmb_count_per_cipher * rp->all_payloads_count;
-    if ((st = dalloc(ctx, &S.weights, S.weight_elems ? S.weight_elems : 1))) { stream_release(ctx); return st; }
-    for (int i = 0; i < 2; ++i) {
-        cudaError_t e = cudaMallocHost((void**)&S.pinned[i], STREAM_CHUNK * STREAM_MSG_BYTES);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&S.dev[i], STREAM_CHUNK * STREAM_MSG_BYTES);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.copied[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) { stream_release(ctx); ctx_fail(ctx, std::string("stream_begin: ") + cudaGetErrorString(e)); return OMR_ERR_ALLOC; }
+    const uint32_t n_idx = rp->max_encode_indices_cipher_count, n_pay = (rp->combination_count + rp->cmb_count_per_cipher - 1) / rp->cmb_count_per_cipher;
+    const size_t words = (size_t)(n_idx + n_pay) * OMR_PV_WORDS;
+    const size_t weight_elems = (size_t)n_pay * rp->cmb_count_per_cipher * rp->all_payloads_count;
+    // a new board with the same layout (the common case: one stream per bulletin-board epoch) keeps its buffers
+    const bool reuse = S.digest && S.n_idx == n_idx && S.n_pay == n_pay && S.weight_elems == weight_elems;
+    if (!reuse) {
+        stream_release(ctx);
+        S.n_idx = n_idx; S.n_pay = n_pay; S.weight_elems = weight_elems;
+        if ((st = dalloc(ctx, &S.digest, words)) || (st = dalloc(ctx, &S.part, words)) || (st = dalloc(ctx, &S.pv, STREAM_CHUNK * OMR_PV_WORDS))) { stream_release(ctx); return st; }
+        if ((st = dalloc(ctx, &S.weights, S.weight_elems ? S.weight_elems : 1))) { stream_release(ctx); return st; }
+        for (int i = 0; i < 2; ++i) {
+            cudaError_t e = cudaMallocHost((void**)&S.pinned[i], STREAM_CHUNK * STREAM_MSG_BYTES);
+            if (e == cudaSuccess) e = cudaMalloc((void**)&S.dev[i], STREAM_CHUNK * STREAM_MSG_BYTES);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.copied[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) { stream_release(ctx); ctx_fail(ctx, std::string("stream_begin: ") + cudaGetErrorString(e)); return OMR_ERR_ALLOC; }
+        }
     }
+    S.active = false; S.rp = *rp; S.index_seed = index_seed; S.index0 = global_index0; S.count = 0; S.next = 0;
     CK(cudaMemsetAsync(S.digest, 0, words * sizeof(u64), s));
     CK(cudaMemsetAsync(S.weights, 0, S.weight_elems * 2, s));                // rows beyond combination_count stay zero (detector.rs:370-371)
     if ((st = weights_from_seed_impl(ctx, weight_seed32, (size_t)rp->combination_count * rp->all_payloads_count, S.weights, 0, s))) { stream_release(ctx); return st; }
