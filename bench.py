@@ -121,6 +121,19 @@ def _pinned(shape, dtype):
     return torch.empty(shape, dtype=dtype).pin_memory()
 
 
+class _StdoutToStderr:
+    """fd-level redirect: libraries that print on stdout (NCCL's version banner when a communicator is created) must not add
+    lines next to the ONE JSON line of the contract"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1); os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1); os.close(self.saved)
+
+
 def _dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
@@ -242,7 +255,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=torch.device(dev))
     board_mode = args.messages_per_step is None
     if board_mode:
         if D_BOARD % world:
@@ -344,7 +358,10 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in (h_a, h_b, h_p)) + 32
     d2h = digest.numel() * 8
 
-    check = multi_gpu_check(omr, torch, dist, np, rank, world, local, dev) if world > 1 else None
+    check = None
+    if world > 1:
+        with _StdoutToStderr():
+            check = multi_gpu_check(omr, torch, dist, np, rank, world, local, dev)
 
     # ---- per-message detect latency (BASELINE.json configs[0]: --payload-count 1): one message, device time ------------
     lat = []

@@ -297,7 +297,8 @@ int omr_mulmod_peak(omr_ctx* ctx, int level, int iters, double* mulmods_per_seco
 int omr_set_latency_shapes(omr_ctx* ctx, int enable);
 
 /* Key switch path.  The LWE key switch (detector.rs:560-563) is a {-1,0,1} x u32 matrix product.  Default: the hand-written
- * CUDA-core kernels (keyswitch_kernel).  Opt-in (enable = 1, or OMR_KS_GEMM=1 in the environment), when the library was built
+ * CUDA-core kernels — keyswitch_dp4a_kernel (digit bits x byte-packed key limbs with IDP.4A; OMR_KS_DP4A=0 falls back to the plain
+ * integer keyswitch_kernel) for large batches, keyswitch_kernel<split rows> for small ones.  Opt-in (enable = 1, or OMR_KS_GEMM=1 in the environment), when the library was built
  * with the CUTLASS headers: an exact int8 tensor-core GEMM (a CUTLASS template instance: int32 accumulation, key split into
  * 8-bit limbs; 74 MB of extra key material built on first use).  Identical results.  Enabling it on a library built without
  * it returns OMR_ERR_STATE.  omr_key_switch_path: 0 = CUDA cores, 1 = tensor-core GEMM. */

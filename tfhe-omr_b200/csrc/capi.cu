@@ -72,6 +72,7 @@ struct omr_ctx {
     int* d_flag = nullptr;                        // "a weight draw was rejected" flag of omr_weights_from_seed_device
     double* l2c_scratch = nullptr;                // partial sums exchanged inside a level-2 cluster
     unsigned long long* ks_part = nullptr;        // [KS_SPLIT_MAXB][KSK_PAD] partial sums of the split key switch
+    uint4* ksd = nullptr; long long* ksd_colsum = nullptr;   // IDP.4A key switch: byte-packed key limbs (77 MB) and the per-column constant
     // packing scratch
     u64* s_partial = nullptr; size_t partial_words = 0;
     u64* s_digest = nullptr; size_t digest_words = 0;
@@ -198,6 +199,12 @@ int launch_ks(omr_ctx* ctx, const u32* rlwe, size_t B, u32* out, cudaStream_t s)
             ks_combine_kernel<<<(unsigned)((nb * (LWE2_N + 1) + 255) / 256), 256, 0, s>>>(r, ctx->ksg_c, out + off * LWE2_STRIDE_IN, (int)nb);
             ctx->launches += 3; CK(cudaGetLastError());
         }
+        return OMR_OK;
+    }
+    if (ctx->ksd) {     // throughput shape: IDP.4A over byte-packed key limbs (keyswitch_kernel<false> stays as the cross-check, OMR_KS_DP4A=0)
+        dim3 dgrid((unsigned)((B + KSD_MB - 1) / KSD_MB), (KSK_PAD + KSD_THREADS - 1) / KSD_THREADS);
+        keyswitch_dp4a_kernel<<<dgrid, KSD_THREADS, KSD_SMEM, s>>>(rlwe, ctx->ksd, ctx->ksd_colsum, out, (int)B);
+        ++ctx->launches; CK(cudaGetLastError());
         return OMR_OK;
     }
     keyswitch_kernel<false><<<grid, KS_THREADS, KS_SMEM, s>>>(rlwe, ctx->ksk, out, (int)B, nullptr);
@@ -509,6 +516,17 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         ksk_pad_kernel<<<(unsigned)((n_ksk_rows * KSK_PAD + 255) / 256), 256, 0, s>>>(tmp, ctx->ksk, n_ksk_rows); ++ctx->launches;
         CKC(cudaStreamSynchronize(s)); cudaFree(tmp);
     }
+    {   // byte-packed limbs + column constant for the IDP.4A key switch
+        const char* e = getenv("OMR_KS_DP4A");
+        if (!e || atoi(e) != 0) {
+            CKC(cudaMalloc((void**)&ctx->ksd, KSD_WORDS * 4)); CKC(cudaMalloc((void**)&ctx->ksd_colsum, KSK_PAD * sizeof(long long)));
+            ksd_build_kernel<<<(unsigned)((KSD_WORDS / 4 + 255) / 256), 256, 0, s>>>(ctx->ksk, ctx->ksd);
+            ksd_colsum_kernel<<<(KSK_PAD + 127) / 128, 128, 0, s>>>(ctx->ksk, ctx->ksd_colsum);
+            ctx->launches += 2; CKC(cudaGetLastError());
+            CKC(cudaStreamSynchronize(s));
+            ctx->key_bytes += KSD_WORDS * 4;
+        }
+    }
     // key switch: the hand-written CUDA-core kernels by default; OMR_KS_GEMM=1 or omr_set_tensor_core_key_switch(ctx, 1) opts into
     // the CUTLASS int8 GEMM (limbs are built then)
     if (const char* e = getenv("OMR_KS_GEMM_MIN")) { long v = atol(e); if (v >= 1) ctx->ksg_min_b = (size_t)v; }
@@ -552,7 +570,7 @@ void omr_ctx_destroy(omr_ctx* ctx) {
     DeviceGuard dg(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_tw1, ctx->d_itw1, ctx->d_tw2, ctx->d_itw2, ctx->d_lut1, ctx->d_lut2, ctx->d_tw2d, ctx->d_itw2d, ctx->bsk1, ctx->ksk, ctx->bsk2, ctx->trk,
-                    ctx->ks_part, ctx->l2c_scratch, ctx->d_flag, ctx->ksg_bt, ctx->ksg_a, ctx->ksg_c, ctx->ksg_ws, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv, ctx->s_coeff};
+                    ctx->ks_part, ctx->ksd, ctx->ksd_colsum, ctx->l2c_scratch, ctx->d_flag, ctx->ksg_bt, ctx->ksg_a, ctx->ksg_c, ctx->ksg_ws, ctx->s_rlwe1, ctx->s_rlwe7, ctx->s_lwe2, ctx->s_ca, ctx->s_cb, ctx->s_partial, ctx->s_digest, ctx->s_payloads, ctx->s_weights, ctx->pv, ctx->s_coeff};
     for (void* p : ptrs) if (p) cudaFree(p);
     stream_release(ctx);
     if (ctx->comm) { if (const NcclApi* api = nccl_api(nullptr)) api->comm_destroy(ctx->comm); ctx->comm = nullptr; }

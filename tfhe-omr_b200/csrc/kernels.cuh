@@ -654,17 +654,113 @@ __global__ void keyswitch_finish_kernel(const u32* __restrict__ rlwe, const unsi
     out[(size_t)m * LWE2_STRIDE_IN + col] = ks_finish((i64)part[e], rlwe[(size_t)m * 2 * F1::N + F1::N], col);
 }
 
+// offset word of the extracted mask coefficient a'_i: every digit of the base-2 decomposition is a bit of it (minus one below the top)
+__device__ __forceinline__ i32 ks_offset_word(const u32* __restrict__ a, int i) {
+    const u32 ai = i == 0 ? a[0] : (a[F1::N - i] ? Q1 - a[F1::N - i] : 0);      // a' = (a0, -a_{N-1}, ..., -a_1)
+    const i32 v = ai > (Q1 >> 1) ? (i32)ai - (i32)Q1 : (i32)ai;
+    return v + ((1 << 26) - 1);                                                  // offset word, base 2, 27 levels
+}
+
+// K2, throughput shape: the same {0,1}-digit x key product on the CUDA cores with IDP.4A (4 multiply-adds per lane-op, full rate on
+// B200: profiles/r2_pipe_microbench.txt).  Balanced base-2 digits of a 27-bit offset word w are d_j = bit_j(w) - 1 (j < 26) and
+// d_26 = bit_26(w), so  SUM_j d_j K_j = SUM_j bit_j(w) K_j - SUM_{j<26} K_j : the second term is a per-column constant of the key
+// (ksd_colsum), the first is a dot product of BITS with the key.  The key is stored as four balanced base-256 limbs, byte-packed over
+// groups of four levels (levels padded 27 -> 28): ksd[(i*7 + g)][col] = uint4 {limb0..limb3}, each u32 = the limb bytes of levels
+// 4g..4g+3 — one coalesced 16-byte load per (coefficient, group, column).  A CTA = 128 columns x 16 messages; the digit bytes of its
+// messages are expanded once per chunk of 64 coefficients into shared memory ([i][g][message] words, read as broadcast 16-byte
+// vectors), so the inner loop is 1 LDG.128 + 4 LDS.128 + 64 IDP.4A per (coefficient, group).  int32 limb sums cannot overflow
+// (28 672 x 128 < 2^31); they recombine to the exact integer keyswitch_kernel accumulates.
+constexpr int KSD_G = 7, KSD_MB = 16, KSD_THREADS = 128, KSD_IC = 64;
+constexpr size_t KSD_WORDS = (size_t)F1::N * KSD_G * KSK_PAD * 4;            // u32 words of the packed key (77 MB)
+constexpr size_t KSD_SMEM = (size_t)KSD_IC * KSD_G * KSD_MB * 4;              // 28 KiB of digit words
+
+__global__ void ksd_build_kernel(const u32* __restrict__ ksk /*[1024*27][KSK_PAD]*/, uint4* __restrict__ ksd) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)F1::N * KSD_G * KSK_PAD) return;
+    const int col = (int)(e % KSK_PAD); const size_t ig = e / KSK_PAD; const int g = (int)(ig % KSD_G), i = (int)(ig / KSD_G);
+    u32 limb[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * g + jj;
+        u32 w = (j < KS_LEVELS && col <= LWE2_N) ? ksk[((size_t)i * KS_LEVELS + j) * KSK_PAD + col] : 0u;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            i32 t = (i32)(w & 255u); w >>= 8;
+            if (t >= 128) { t -= 256; w += 1; }
+            limb[l] |= (u32)(t & 0xFF) << (8 * jj);
+        }
+    }
+    ksd[e] = make_uint4(limb[0], limb[1], limb[2], limb[3]);
+}
+// colsum[col] = SUM_i SUM_{j<26} KSK[i][j][col]
+__global__ void ksd_colsum_kernel(const u32* __restrict__ ksk, long long* __restrict__ colsum) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= KSK_PAD) return;
+    long long s = 0;
+    for (int i = 0; i < F1::N; ++i)
+        for (int j = 0; j < KS_LEVELS - 1; ++j) s += (long long)ksk[((size_t)i * KS_LEVELS + j) * KSK_PAD + col];
+    colsum[col] = s;
+}
+__global__ void __launch_bounds__(KSD_THREADS)
+keyswitch_dp4a_kernel(const u32* __restrict__ rlwe, const uint4* __restrict__ ksd, const long long* __restrict__ colsum, u32* __restrict__ out, int B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32* dw = reinterpret_cast<u32*>(smem_raw);                               // [KSD_IC][KSD_G][KSD_MB]
+    const int m0 = blockIdx.x * KSD_MB, col = blockIdx.y * KSD_THREADS + threadIdx.x;
+    const bool live = col < KSK_PAD;
+    i32 acc[KSD_MB][4];
+#pragma unroll
+    for (int m = 0; m < KSD_MB; ++m) { acc[m][0] = 0; acc[m][1] = 0; acc[m][2] = 0; acc[m][3] = 0; }
+#pragma unroll 1
+    for (int i0 = 0; i0 < F1::N; i0 += KSD_IC) {
+        __syncthreads();                                                      // the previous chunk's digits have been consumed
+        for (int e = threadIdx.x; e < KSD_IC * KSD_MB; e += KSD_THREADS) {
+            const int m = e % KSD_MB, il = e / KSD_MB;
+            u32 w = 0;                                                        // a message beyond the batch contributes nothing
+            if (m0 + m < B) w = (u32)ks_offset_word(rlwe + (size_t)(m0 + m) * 2 * F1::N, i0 + il);
+#pragma unroll
+            for (int g = 0; g < KSD_G; ++g) dw[(il * KSD_G + g) * KSD_MB + m] = (((w >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
+        }
+        __syncthreads();
+        if (live) {
+            const uint4* kp = ksd + (size_t)i0 * KSD_G * KSK_PAD + col;
+#pragma unroll 1
+            for (int il = 0; il < KSD_IC; ++il) {
+#pragma unroll
+                for (int g = 0; g < KSD_G; ++g) {
+                    const uint4 kk = __ldg(kp + (size_t)(il * KSD_G + g) * KSK_PAD);
+                    const uint4* d4 = reinterpret_cast<const uint4*>(dw + (il * KSD_G + g) * KSD_MB);
+#pragma unroll
+                    for (int q = 0; q < KSD_MB / 4; ++q) {
+                        const uint4 dv = d4[q];
+                        const u32 dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            acc[4 * q + r][0] = __dp4a((int)dd[r], (int)kk.x, acc[4 * q + r][0]);
+                            acc[4 * q + r][1] = __dp4a((int)dd[r], (int)kk.y, acc[4 * q + r][1]);
+                            acc[4 * q + r][2] = __dp4a((int)dd[r], (int)kk.z, acc[4 * q + r][2]);
+                            acc[4 * q + r][3] = __dp4a((int)dd[r], (int)kk.w, acc[4 * q + r][3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!live || col > LWE2_N) return;
+    const i64 cs = colsum[col];
+#pragma unroll
+    for (int m = 0; m < KSD_MB; ++m) {
+        if (m0 + m >= B) break;
+        const i64 sum = (i64)acc[m][0] + (i64)acc[m][1] * 256 + (i64)acc[m][2] * 65536 + (i64)acc[m][3] * 16777216 - cs;
+        out[(size_t)(m0 + m) * LWE2_STRIDE_IN + col] = ks_finish(sum, rlwe[(size_t)(m0 + m) * 2 * F1::N + F1::N], col);
+    }
+}
+
 // K2 as a tensor-core GEMM (ks_gemm.cu): operand expansion and the epilogue.  K index = i * 27 + j, N index = col * 4 + limb.
 constexpr int KSG_K = F1::N * KS_LEVELS;                     // 27 648
 constexpr size_t KSG_MIN_B = 1, KSG_CHUNK = 2048;            // faster than the CUDA-core kernels at every batch size; 2 048 messages per GEMM (79 MB of scratch)
 constexpr int KSG_LIMBS = 4, KSG_N = ((LWE2_N + 1) * KSG_LIMBS + 15) / 16 * 16;   // 2 688
 // A[m][i*27 + j] = balanced base-2 digit j of the extracted mask coefficient a'_i (the same digits keyswitch_kernel uses).
 // One thread writes 16 consecutive bytes of a row (coalesced 16-byte stores); they span at most two coefficients.
-__device__ __forceinline__ i32 ks_offset_word(const u32* __restrict__ a, int i) {
-    const u32 ai = i == 0 ? a[0] : (a[F1::N - i] ? Q1 - a[F1::N - i] : 0);      // a' = (a0, -a_{N-1}, ..., -a_1)
-    const i32 v = ai > (Q1 >> 1) ? (i32)ai - (i32)Q1 : (i32)ai;
-    return v + ((1 << 26) - 1);                                                  // offset word, base 2, 27 levels
-}
 __global__ void ks_digits_kernel(const u32* __restrict__ rlwe, signed char* __restrict__ A, int B) {
     constexpr int CH = KSG_K / 16;                                               // 1 728 chunks of 16 bytes per message
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
