@@ -109,9 +109,7 @@ class Detector:
         st = create(self.device, C.byref(blobs), C.byref(h))
         if st != _lib.OMR_OK:
             raise OmrError(st, (self.L.omr_last_error(None) or b"").decode())
-        self.h = h
-        if on_device:
-            pass    # omr_ctx_create_device_keys drains the device before copying (the tensors may come from any torch stream)
+        self.h = h          # (omr_ctx_create_device_keys drains the device before copying: the tensors may come from any torch stream)
 
     @classmethod
     def from_blob(cls, path, device=None):
