@@ -19,6 +19,12 @@ typedef unsigned __int128 u128;
 constexpr u32 Q1 = 134215681u;
 constexpr u64 Q2 = 1125899906826241ull;
 
+// ptxas balances integer adds and moves between the ALU pipe and the FMA pipe (IMAD.IADD, IMAD.MOV) as if IMAD could issue on both
+// FMA halves; on B200 every IMAD runs on the heavy half only (ncu: fmalite 0.02 % in the level-1 kernel), the pipe that bounds
+// that kernel.  A three-input add cannot be an IMAD: adding this opaque zero (a constant-bank operand: no register, no extra
+// instruction) keeps an addition on the ALU pipe.
+__constant__ uint32_t c_opaque_zero = 0;
+
 // ---- level 1: 32-bit ---------------------------------------------------------------------------------------------
 struct F1 {
     typedef u32 T;
@@ -38,6 +44,7 @@ struct F1 {
     static __device__ __forceinline__ T fold(T x) { return (x & ((1u << 27) - 1)) + (x >> 27) * 2047u; }
     static __device__ __forceinline__ T csub(T x, T m) { return min(x, x - m); }   // x < 2m -> x mod-ish m
     static __device__ __forceinline__ T canon_lazy(T x) { return csub(fold(x), Q); } // x < 32q -> [0,q)
+    static __device__ __forceinline__ T add_alu(T a, T b) { return a + b + c_opaque_zero; }    // IADD3 on the ALU pipe, never IMAD.IADD
     static __device__ __forceinline__ void mac(Acc& acc, T x, T k) { acc += (u64)x * k; }
     // Montgomery REDC: acc < 2^62 -> acc * 2^-32 mod q, lazily in [0, acc/2^32 + q)
     static __device__ __forceinline__ T redc(Acc acc) {
@@ -45,11 +52,11 @@ struct F1 {
         return (T)((acc + (u64)m * Q) >> 32);
     }
     // inverse-NTT butterfly support: keep sums < 2q
-    static __device__ __forceinline__ T inv_add(T x, T y, int) { T s = x + y; return min(s, s - 2 * Q); }
+    static __device__ __forceinline__ T inv_add(T x, T y, int) { T s = add_alu(x, y); return min(s, s - 2 * Q); }
     static __device__ __forceinline__ T inv_sub(T x, T y, int) { return x - y + 2 * Q; }
     static __device__ __forceinline__ T inv_prepare(T x) { return fold(x); }        // redc output (<8q) -> < 2q
     // acc (canonical) + delta (inverse output, < 2q) -> canonical
-    static __device__ __forceinline__ T add_canon(T a, T d) { T v = a + d; v = csub(v, 2 * Q); return csub(v, Q); }
+    static __device__ __forceinline__ T add_canon(T a, T d) { T v = add_alu(a, d); v = csub(v, 2 * Q); return csub(v, Q); }
 };
 
 // ---- level 2: 64-bit ---------------------------------------------------------------------------------------------
@@ -71,6 +78,7 @@ struct F2 {
     static __device__ __forceinline__ T fold(T x) { return (x & ((1ull << 50) - 1)) + (x >> 50) * 16383ull; }
     static __device__ __forceinline__ T csub(T x, T m) { return x >= m ? x - m : x; }
     static __device__ __forceinline__ T canon_lazy(T x) { return csub(fold(x), Q); }
+    static __device__ __forceinline__ T add_alu(T a, T b) { return a + b; }
     static __device__ __forceinline__ void mac(Acc& acc, T x, T k) {
         u64 lo = x * k, hi = __umul64hi(x, k);
         acc.lo += lo; acc.hi += hi + (acc.lo < lo);

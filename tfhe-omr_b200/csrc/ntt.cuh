@@ -103,7 +103,7 @@ template <class F> struct ArInt {
     template <int S0, int E> static __device__ __forceinline__ void pre_fwd(T (&)[E]) {}
     template <int STAGE> static __device__ __forceinline__ void fwd(T& a, T& b, TW w) {
         const T u = a, v = F::mul_shoup(b, w);
-        a = u + v; b = u - v + 2 * F::Q;
+        a = F::add_alu(u, v); b = u - v + 2 * F::Q;
     }
     template <int STAGE> static __device__ __forceinline__ void inv(T& a, T& b, TW w) {
         constexpr int done = LOGN - 1 - STAGE;                 // Gentleman-Sande stages completed before this one
