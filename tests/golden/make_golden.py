@@ -52,6 +52,33 @@ def compute():
     return out
 
 
+# ---- v2: the counter-based (ChaCha12) generators — detection key and clues — for a fixed secret and seed -------------------
+KG_SECRET_SEED, KG_SEED, CLUE_CB_SEED = 0x4F4D520003, bytes(range(50, 82)), bytes(range(90, 122))
+
+
+def inputs_v2():
+    kp = O.KeyPack(seed=KG_SECRET_SEED)
+    msgs = np.random.default_rng(9).integers(0, 8, (3, 7), dtype=np.uint8)
+    return kp, msgs
+
+
+def compute_v2():
+    kp, msgs = inputs_v2()
+    ref = O.KeyPack(cb_from=kp, cb_seed=KG_SEED)
+    out = {}
+    for name, arr in (("bsk1", ref.bsk1), ("ksk", ref.ksk), ("bsk2", ref.bsk2), ("trace", ref.trk)):
+        out[name + "_sha"] = sha(arr)
+        out[name + "_head"] = np.ascontiguousarray(arr).reshape(-1)[:16].copy()
+        out[name + "_tail"] = np.ascontiguousarray(arr).reshape(-1)[-16:].copy()
+    a, b = kp.gen_clues_cb(CLUE_CB_SEED, 3, index0=70000, msgs=msgs)
+    out["clue_a"], out["clue_b"] = a, b
+    out["secrets"] = np.concatenate([x.astype(np.int32) for x in kp.secrets()])
+    pa, pb = kp.clue_key()
+    out["clue_key"] = np.stack([pa, pb])
+    return out
+
+
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "golden_v1.npz"), **compute())
-    print("wrote golden_v1.npz")
+    np.savez_compressed(os.path.join(HERE, "golden_v2.npz"), **compute_v2())
+    print("wrote golden_v1.npz, golden_v2.npz")

@@ -55,3 +55,32 @@ def test_gpu_reproduces_golden():
     det2 = omr.Detector(omr.DetectionKey(kb1, dev(ksk, np.int32), kb2, kt, coeff_domain=True), device=0)
     pv2 = det2.detect((dev(a, np.int16), dev(b, np.int16)))
     assert np.array_equal(G.sha(pv2.to_host()), GOLD["pv_sha"])
+
+
+GOLD2 = dict(np.load(os.path.join(HERE, "golden", "golden_v2.npz")))
+
+
+def test_oracle_reproduces_golden_v2():
+    """the counter-based generators (ChaCha12 streams, integer Gaussian tables) are pinned against silent convention drift"""
+    out = G.compute_v2()
+    assert set(out) == set(GOLD2)
+    for k, v in out.items():
+        assert np.array_equal(v, GOLD2[k]), k
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_v2():
+    """GPU detection-key generation and clue generation reproduce the fixtures from the stored secrets / clue key alone (no oracle)"""
+    import hashlib
+    import tfhe_omr_b200 as omr
+    sec = GOLD2["secrets"]
+    secrets = (sec[:512], sec[512:1536], sec[1536:2206], sec[2206:])
+    det = omr.Detector.generate(secrets, G.KG_SEED, device=0, want_keys=True)
+    dk = det.detection_key
+    for name, arr in (("bsk1", dk.bsk1), ("ksk", dk.ksk), ("bsk2", dk.bsk2), ("trace", dk.trace)):
+        assert np.array_equal(np.frombuffer(hashlib.sha256(np.ascontiguousarray(arr).tobytes()).digest(), np.uint8), GOLD2[name + "_sha"]), name
+        assert np.array_equal(arr.reshape(-1)[:16], GOLD2[name + "_head"]) and np.array_equal(arr.reshape(-1)[-16:], GOLD2[name + "_tail"])
+    msgs = np.random.default_rng(9).integers(0, 8, (3, 7), dtype=np.uint8)
+    a, b = det.gen_clues((GOLD2["clue_key"][0], GOLD2["clue_key"][1]), 3, seed=G.CLUE_CB_SEED, index0=70000, msgs=msgs)
+    assert np.array_equal(a.cpu().numpy().view(np.uint16), GOLD2["clue_a"]) and np.array_equal(b.cpu().numpy().view(np.uint16), GOLD2["clue_b"])
+    det.close()
