@@ -7,7 +7,7 @@
     python bench.py --messages-per-step M ...                 (slice mode: M messages per rank per step, weak scaling)
 
 One step = one pass of the hot path over the WHOLE 65 536-message board: every rank detects its D/N messages in chunks
-of <= 16 384, packs each chunk into the index and payload digests and folds them into a running digest (omr_digest_add_mod)
+(--chunk, default 16 384), packs each chunk into the index and payload digests and folds them into a running digest (omr_digest_add_mod)
 — all inside the timed region — and the N partial digests are summed over NCCL (the only collective).  Strong scaling: the
 board is fixed, `value` = 65 536 / step time.
 `value` times the step with inputs resident in HBM; `e2e` times the same board through the host-buffer C ABI
@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 D_BOARD = 65536
 PERTINENT = 50
-CHUNK = 16384                                            # messages per detect launch (bounds the scratch: 16 384 x 32 KiB of pertinency vector)
+CHUNK = 16384                                            # messages per detect launch (--chunk); 16 384 x 32 KiB of pertinency vector per chunk
 Q1, Q2 = 134215681, 1125899906826241
 METRIC = "detected messages/sec at D=65536"
 README_SINGLE_CORE_MSGS = 65536 / 15340.2083335          # /root/reference README.md:120-121 -> 4.272 msg/s
@@ -286,7 +286,7 @@ def run_ours(args):
         h.copy_(d)
     h_digest = _pinned(digest.shape, digest.dtype)
     torch.cuda.synchronize()
-    chunk = min(CHUNK, M)
+    chunk = min(args.chunk, M)
 
     def step_resident(i, t=None):
         index0 = ((i * world + rank) % n_slices) * M          # board mode: rank * M
@@ -664,6 +664,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="board65536", choices=["board65536", "pack4096"])
     ap.add_argument("--messages-per-step", type=int, default=None, help="slice mode: messages per rank per step (weak scaling); default = the whole board / N")
+    ap.add_argument("--chunk", type=int, default=CHUNK, help="messages per detect launch; the partial digests of the chunks are folded into a running digest")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -277,7 +277,7 @@ int detect_device(omr_ctx* ctx, const unsigned short* d_ca, const unsigned short
     int st;
     if (times) *times = omr_stage_times{};
     if (!B) return OMR_OK;
-    const size_t MAXB = 16384;
+    const size_t MAXB = 16384;          // (one launch per kernel for a whole 65 536 board was measured: no faster end to end, 4.3 GB of scratch)
     if ((st = ensure_scratch(ctx, B < MAXB ? B : MAXB))) return st;
     for (size_t off = 0; off < B; off += MAXB) {
         const size_t nb = B - off < MAXB ? B - off : MAXB;
