@@ -96,6 +96,9 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.time() + 3.0                     # a very short timed region: wait for the first sample rather than report none
+        while not self.rows and time.time() < t_end:
+            time.sleep(0.05)
         time.sleep(0.25)
         self.proc.terminate()
         try:
