@@ -232,3 +232,16 @@ def test_gpu_detection_key_generation(keypack, decoy):
         s0, z1, s2, z2 = keypack.secrets()
         omr.Detector.generate((s0 + 2, z1, s2, z2), seed, device=0)
     det.close()
+
+
+def test_omr_example_end_to_end(capsys):
+    """examples/omr.py — the reference's examples/omr.rs driver on the GPU — at a small board, product API only"""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("omr_example", os.path.join(root, "examples", "omr.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    assert mod.main(["-p", "300"]) == 0
+    out = capsys.readouterr().out
+    assert "All done" in out and "detect time per message" in out and "decode time" in out
+    assert mod.main(["-p", "1"]) == 0                        # BASELINE.json configs[0]: one message, three index ciphertexts
