@@ -808,7 +808,7 @@ __global__ void ks_combine_kernel(const u32* __restrict__ rlwe, const i32* __res
 // The 11 x 25 digit transforms, the MAC against the trace key and the inverse transforms run on the FP64 pipe like K3
 // (two digits per pass, key words = centred doubles x N^-1); the two final forward transforms (to_ntt_rlwe) stay integer.
 constexpr int TR_THREADS = GeoL2::NT;
-constexpr size_t TR_SMEM = (size_t)2 * F2::N * 8 + (size_t)2 * GeoL2::BUF * 8;
+constexpr size_t TR_SMEM = (size_t)2 * F2::N * 8 + (size_t)2 * GeoL2::BUF * 8 + F2::N * sizeof(double2);   // acc, two exchange buffers, forward twiddles
 
 // sigma_d(p)[pos] as a signed value: source index i0 = pos * d^-1 mod 2N
 __device__ __forceinline__ i64 automorphed(const u64* p, int pos, u32 dinv) {
@@ -823,7 +823,9 @@ trace_kernel(u64* __restrict__ ct, const double* __restrict__ trk, Tables tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* acc = reinterpret_cast<u64*>(smem_raw);        // [2][N]: a, b (canonical)
     double* bx = reinterpret_cast<double*>(acc + 2 * N); double* by = bx + GEO::BUF;
+    double2* s_tw = reinterpret_cast<double2*>(by + GEO::BUF);          // de-interleaved forward twiddles, as in K3
     const int t = threadIdx.x;
+    fill_twiddles_deint<GEO>(s_tw, tb.tw2d, t, TR_THREADS);
     u64* g = ct + (size_t)blockIdx.x * 2 * N;
     for (int e = t; e < 2 * N; e += TR_THREADS) acc[e] = F::csub(F::mul_shoup(g[e], tb.n2_inv), F::Q);   // detector.rs:635-636
     __syncthreads();
@@ -852,7 +854,7 @@ trace_kernel(u64* __restrict__ ct, const double* __restrict__ trk, Tables tb) {
                 x[k] = D2::from_small(gadget_digit_signed<F, GT>(u[k], r));
                 y[k] = pair ? D2::from_small(gadget_digit_signed<F, GT>(u[k], r + 1)) : 0.0;
             }
-            ntt_forward2s<AR, GEO, LdGlobal>(x, y, bx, by, tb.tw2d, t, 0);
+            ntt_forward2s<AR, GEO, LdSharedD>(x, y, bx, by, s_tw, t, 0);
             const double* kx = key + (size_t)r * 2 * N;
             const double* ky = kx + (pair ? 2 * N : 0);                   // (single: y = NTT(0) = 0, any key row)
 #pragma unroll
