@@ -67,7 +67,7 @@ def test_stages_bit_exact(detector, keypack, decoy, shape):
 
 def test_launch_shapes_agree(detector, keypack):
     """Latency and throughput shapes of every stage give identical words on random (not clue-shaped) inputs, including
-    batch sizes around the switch-over points (level 1: one rotation per CTA in one or several waves / four / eight per CTA;
+    batch sizes around the switch-over points (level 1: one rotation per CTA in one or several waves / four / six per CTA;
     level 2: clusters up to ~44 messages, 512-thread CTAs, 256-thread CTAs; key switch: split rows up to 256 messages)."""
     import torch
     rng = np.random.default_rng(5)

@@ -245,12 +245,13 @@ int launch_trace(omr_ctx* ctx, u64* ct, size_t B, cudaStream_t s) {
 // L1 kernel into caller-provided per-clue buffer (no internal allocation); the shape follows the number of blind rotations
 int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* cb, size_t B, u32* rlwe7, u32* out, cudaStream_t s) {
     const size_t n_clues = B * CLUE_COUNT;
-    // Shape = rotations per CTA (1 = the 8-groups-per-rotation latency kernel).  One wave of n_sm CTAs takes about 2.6 / 7.4 /
-    // 13.2 ms for 1 / 4 / 8 rotations per CTA (2 per CTA, 5.4 ms, never beats two waves of the latency kernel); small and mid-size batches take the shape with the shortest sum of
-    // whole waves, large ones (where the tail wave is negligible) the 8-rotation shape with the best per-rotation cost.
-    int shape = 8;
+    // Shape = rotations per CTA (1 = the 8-groups-per-rotation latency kernel).  One wave of n_sm CTAs takes about 2.6 / 6.5 /
+    // 8.7 ms for 1 / 4 / 6 rotations per CTA; small and mid-size batches take the shape with the shortest sum of whole waves,
+    // large ones (where the tail wave is negligible) the 6-rotation shape with the best per-rotation cost: 12 warps at 168
+    // registers beat 16 warps at 128 (spills) by 7 % (profiles/r2_ab_l1_slots6_two_digits.txt).
+    int shape = 6;
     if (ctx->latency_shapes && n_clues <= 16 * (size_t)ctx->n_sm) {
-        const int slots[3] = {1, 4, 8}, wave_us[3] = {2600, 7400, 13200};
+        const int slots[3] = {1, 4, 6}, wave_us[3] = {2600, 6530, 8670};
         size_t best = ~(size_t)0;
         for (int k = 0; k < 3; ++k) {
             const size_t ctas = (n_clues + slots[k] - 1) / slots[k], waves = (ctas + ctx->n_sm - 1) / ctx->n_sm, cost = waves * wave_us[k];
@@ -262,7 +263,7 @@ int launch_l1_raw(omr_ctx* ctx, const unsigned short* ca, const unsigned short* 
     else if (shape == 4)
         l1_blind_rotate_kernel<4><<<(unsigned)((n_clues + 3) / 4), L1Cfg<4>::THREADS, L1Cfg<4>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     else
-        l1_blind_rotate_kernel<8><<<(unsigned)((n_clues + 7) / 8), L1Cfg<8>::THREADS, L1Cfg<8>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
+        l1_blind_rotate_kernel<6><<<(unsigned)((n_clues + 5) / 6), L1Cfg<6>::THREADS, L1Cfg<6>::SMEM, s>>>(ca, cb, ctx->bsk1, rlwe7, (int)n_clues, ctx->tb);
     ++ctx->launches; CK(cudaGetLastError());
     sum7_kernel<<<(unsigned)((B * 2 * F1::N + 255) / 256), 256, 0, s>>>(rlwe7, out, B);
     ++ctx->launches; CK(cudaGetLastError());
@@ -431,13 +432,13 @@ int create_impl(int device, const omr_key_blobs* keys, bool keys_on_device, omr_
         CKC(cudaMemcpyToSymbol(c_tw1_head, h1, sizeof h1));
         CKC(cudaMemcpyToSymbol(c_tw2d_head, h2, sizeof h2));
     }
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<8>::SMEM));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<6>::SMEM));
     CKC(cudaFuncSetAttribute(l1_blind_rotate_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1L_SMEM));
     CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L1Cfg<4>::SMEM));
     { cudaDeviceProp prop; CKC(cudaGetDeviceProperties(&prop, device)); ctx->n_sm = prop.multiProcessorCount; }
     // always carve out the maximum shared memory for the big kernels: with the driver's default heuristic an occasional
     // launch of l2_blind_rotate_kernel got a smaller carve-out and ran at 1 CTA/SM (278 ms instead of 215 ms for 2 368 messages)
-    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(l1_blind_rotate_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(l2_blind_rotate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(keyswitch_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -119,27 +119,32 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, u32 bytes, 
 }
 
 // ---- K1: first-level blind rotations ---------------------------------------------------------------------------------
-// A CTA runs 8 blind rotations at once — 8 consecutive (message, clue) pairs of the batch — one per group of 64 threads
-// (2 warps, 16 coefficients per thread): 16 warps = 4 per scheduler, and every blind rotation walks the same key
-// sequence BSK1[0..511], so per CMux step the 64 KiB RGSW tile is staged ONCE into shared memory by a TMA bulk copy and
-// reused by all 8 groups; the copy of tile i+1 is in flight while the groups run their inverse transforms and the first
-// forward transform of the next step.  Twiddles live in shared memory.  Clue extraction (CmLwe::extract_all,
+// A CTA runs 6 blind rotations at once — 6 consecutive (message, clue) pairs of the batch — one per group of 64 threads
+// (2 warps, 16 coefficients per thread): 12 warps = 3 per SM partition at 168 registers, which holds the 32 u64 MAC
+// accumulators AND two digit transforms in flight without the spills of the 16-warp / 128-register shape (measured: 8 groups
+// 1 206 ms, 6 groups 1 155 ms, 6 groups with two digits per pass 1 120 ms per 16 384 messages).  Every blind rotation walks the
+// same key sequence BSK1[0..511], so per CMux step the 64 KiB RGSW tile is staged ONCE into shared memory by a TMA bulk copy and
+// reused by all groups; the copy of tile i+1 is in flight while the groups run their inverse transforms and the first
+// forward transforms of the next step.  Twiddles live in shared memory.  Clue extraction (CmLwe::extract_all,
 // detector.rs:514) is index arithmetic on the fly.  Output: one RLWE accumulator per (message, clue); sum7_kernel adds
 // the 7 accumulators of a message (add_element_wise, detector.rs:556).
 constexpr int L1_GROUP = GeoL1::NT;                        // 64
 constexpr int L1_TILE_WORDS = 2 * G1::LEVELS * 2 * F1::N;  // 16384 u32 = 64 KiB
 constexpr int L1_GROUP_WORDS = 2 * F1::N + 2 * GeoL1::BUF;
-// SLOTS = blind rotations per CTA: 8 fills an SM (512 threads); 4 serves mid-size batches that could not give every SM an
-// 8-rotation CTA (capi.cu: launch_l1_raw).
+// SLOTS = blind rotations per CTA: 6 is the throughput shape (384 threads); 4 serves mid-size batches that could not give every SM a
+// 6-rotation CTA (capi.cu: launch_l1_raw).
 template <int SLOTS> struct L1Cfg {
     static constexpr int THREADS = SLOTS * L1_GROUP;
+    // one CTA per SM: each of the 4 SM partitions holds ceil(warps / 4) warps and 16 384 registers (allocated 8 per thread at a time)
+    static constexpr int WARPS_PER_PARTITION = (THREADS / 32 + 3) / 4;
+    static constexpr int MAXREG = (16384 / (32 * WARPS_PER_PARTITION)) / 8 * 8 > 248 ? 248 : (16384 / (32 * WARPS_PER_PARTITION)) / 8 * 8;
     static constexpr int TILE_WORDS = L1_TILE_WORDS;
     static constexpr size_t SMEM = (size_t)TILE_WORDS * 4 + 2 * F1::N * sizeof(uint2) + (size_t)SLOTS * L1_GROUP_WORDS * 4 +
                                    (size_t)SLOTS * CLUE_N * sizeof(unsigned short) + 16;
 };
 
 template <int SLOTS>
-__global__ void __launch_bounds__(SLOTS * L1_GROUP, 1)
+__global__ void __maxnreg__(L1Cfg<SLOTS>::MAXREG)
 l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned short* __restrict__ clue_b,
                        const u32* __restrict__ bsk1, u32* __restrict__ out /*[n_clues][2][N]*/, int n_clues, Tables tb) {
     typedef F1 F; typedef G1 G; typedef GeoL1 GEO; typedef ArInt<F1> AR; typedef L1Cfg<SLOTS> CFG;
@@ -183,11 +188,11 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
             i32 u[E];
             decompose_words<F, G, GEO>(u, acc + p * N, a, t);
 #pragma unroll
-            for (int r = 0; r < L; ++r) {
-                u32 x[E];
+            for (int r = 0; r < L; r += 2) {
+                u32 x[E], y[E];
 #pragma unroll
-                for (int k = 0; k < E; ++k) x[k] = gadget_digit<F, G>(u[k], r);
-                ntt_forward<AR, GEO, LdSharedD>(x, eb, s_tw, t, bar);
+                for (int k = 0; k < E; ++k) { x[k] = gadget_digit<F, G>(u[k], r); y[k] = gadget_digit<F, G>(u[k], r + 1); }
+                ntt_forward2s<AR, GEO, LdSharedD>(x, y, eb.a, eb.b, s_tw, t, bar);      // two digits in flight: twice the ILP
                 if (r == 0 && p == 0) { mbar_wait(mbar, phase & 1); ++phase; }             // tile i has landed
                 const u32* ka = ktile + (size_t)(p * L + r) * 2 * N + out_idx<GEO>(t, 0);
                 const u32* kb = ka + N;
@@ -197,6 +202,9 @@ l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned
                     const uint4 va = *reinterpret_cast<const uint4*>(ka + o), vb = *reinterpret_cast<const uint4*>(kb + o);
                     F::mac(ma[k], x[k], va.x); F::mac(ma[k + 1], x[k + 1], va.y); F::mac(ma[k + 2], x[k + 2], va.z); F::mac(ma[k + 3], x[k + 3], va.w);
                     F::mac(mb[k], x[k], vb.x); F::mac(mb[k + 1], x[k + 1], vb.y); F::mac(mb[k + 2], x[k + 2], vb.z); F::mac(mb[k + 3], x[k + 3], vb.w);
+                    const uint4 wa = *reinterpret_cast<const uint4*>(ka + 2 * N + o), wb = *reinterpret_cast<const uint4*>(kb + 2 * N + o);
+                    F::mac(ma[k], y[k], wa.x); F::mac(ma[k + 1], y[k + 1], wa.y); F::mac(ma[k + 2], y[k + 2], wa.z); F::mac(ma[k + 3], y[k + 3], wa.w);
+                    F::mac(mb[k], y[k], wb.x); F::mac(mb[k + 1], y[k + 1], wb.y); F::mac(mb[k + 2], y[k + 2], wb.z); F::mac(mb[k + 3], y[k + 3], wb.w);
                 }
             }
         }
