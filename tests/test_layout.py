@@ -89,6 +89,8 @@ def test_no_exchange_hazards_under_arbitrary_warp_interleavings():
     for name, prog in progs.items():
         assert LC.race_check("L2", prog, schedules=25) is None, name
     assert LC.race_check("L1", ["F", "I", "I2", "F"], schedules=5) is None
+    # K1 step: four digit pairs through the two buffers, the CTA barrier, both inverse transforms, the group barrier
+    assert LC.race_check("L1", (["F2"] * 4 + ["B", "I2", "B"]) * 2, schedules=10) is None, "K1 step"
     # the detector itself: the unpadded first exchange lets warp w's private region overlap warp w+1's and must be flagged
     saved = LC.CONFIGS["L2"]
     try:
