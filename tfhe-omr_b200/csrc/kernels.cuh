@@ -143,6 +143,8 @@ template <int SLOTS> struct L1Cfg {
                                    (size_t)SLOTS * CLUE_N * sizeof(unsigned short) + 16;
 };
 
+static_assert(L1Cfg<6>::MAXREG == 168 && L1Cfg<4>::MAXREG == 248 && L1Cfg<8>::MAXREG == 128, "registers per thread follow the warps per SM partition");
+static_assert(L1Cfg<6>::SMEM <= 227 * 1024, "one CTA per SM");
 template <int SLOTS>
 __global__ void __maxnreg__(L1Cfg<SLOTS>::MAXREG)
 l1_blind_rotate_kernel(const unsigned short* __restrict__ clue_a, const unsigned short* __restrict__ clue_b,
