@@ -155,6 +155,17 @@ def _random_detector(omr, torch, dev, local):
 
 
 # ---- harness-side key material for the checks that must decode (numpy; the product makes the detection key and the clues) -------
+def workload_config(world, M, chunk, n_idx, n_pay, key_switch):
+    """`config` of the contract line: the workload both arms are quoted on (the reference arm prints the same dictionary and says in
+    `sample` / `cpu_baseline.sample` which bounded part of it one CPU step runs)"""
+    return {"workload": WORKLOAD, "D": D_BOARD, "messages_per_step": world * M, "messages_per_step_per_gpu": M, "chunk": chunk, "pertinent": PERTINENT,
+            "index_ciphertexts": n_idx, "payload_ciphertexts": n_pay,
+            "parallelism": f"message-sharded x{world} (rank r detects and packs messages [r D/N, (r+1) D/N)), keys replicated, NCCL sum of partial digests",
+            "key_switch": key_switch,
+            "l2": "per-step working set (keys 363 MiB + %d MiB of pertinency vector per chunk) exceeds the 126 MB L2; no flush" % (chunk * 32768 // 2**20),
+            "vs_baseline_ref": "reference README.md:120-121, single-core detect 4.272 msg/s (unnamed AVX-512 CPU)"}
+
+
 def _recipient(np, seed):
     """secrets of a recipient and its clue public key (pa, pb = pa*s0 + e over Z_2048[X]/(X^512+1))"""
     rng = np.random.default_rng(seed)
@@ -412,12 +423,7 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 2), "unit": "messages/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong" if board_mode else "weak",
         "vs_baseline": round(value / README_SINGLE_CORE_MSGS, 2), "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "D": D_BOARD, "messages_per_step": world * M,
-                   "messages_per_step_per_gpu": M, "chunk": chunk, "pertinent": PERTINENT, "index_ciphertexts": n_idx, "payload_ciphertexts": n_pay,
-                   "parallelism": f"message-sharded x{world} (rank r detects and packs messages [r D/N, (r+1) D/N)), keys replicated, NCCL sum of partial digests",
-                   "key_switch": det.key_switch_path(),
-                   "l2": "per-step working set (keys 363 MiB + %d MiB of pertinency vector per chunk) exceeds the 126 MB L2; no flush" % (chunk * 32768 // 2**20),
-                   "vs_baseline_ref": "reference README.md:120-121, single-core detect 4.272 msg/s (unnamed AVX-512 CPU)"},
+        "config": workload_config(world, M, chunk, n_idx, n_pay, det.key_switch_path()),
         "e2e": {"value": round(e2e_value, 2), "unit": "messages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "api": "omr_stream_begin / omr_stream_push / omr_stream_snapshot (pinned host clues + payloads in, digest out)"},
         "gpu_launches": int(launches),
@@ -530,16 +536,19 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    M_arm = D_BOARD // world if args.messages_per_step is None else args.messages_per_step
     desc = (f"oracle port of detect + both packers (C++, {'-march=native' if native else 'portable'}) on {sample} messages of the board per step, {cores} threads "
             f"(one message per thread, examples/omr.rs:160-164)")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "messages/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "messages/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
         "scaling": "strong" if args.messages_per_step is None else "weak",
         "vs_baseline": round(value / README_SINGLE_CORE_MSGS, 3), "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "D": D_BOARD, "messages_per_step": sample,
-                   "messages_per_step_per_gpu": sample, "pertinent": PERTINENT, "index_ciphertexts": n_idx, "payload_ciphertexts": n_pay,
-                   "parallelism": f"{cores} host threads, one message per thread"},
+        # the GPU arm's config for the same launch (the workload both arms are quoted on); what one CPU step actually runs is `sample`
+        "config": workload_config(world, M_arm, min(args.chunk, M_arm), n_idx, n_pay,
+                                  "tensor-core" if os.environ.get("OMR_KS_GEMM") == "1" else "cuda-core"),
+        "sample": {"messages_per_step": sample, "host_threads": cores, "parallelism": f"{cores} host threads, one message per thread"},
         "cpu_baseline": {"value": round(value, 3), "unit": "messages/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": round(value, 3), "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

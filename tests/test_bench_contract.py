@@ -38,6 +38,11 @@ def test_reference_arm_line():
     assert d["scaling"] == "strong" and d["metric"] == "detected messages/sec at D=65536" and d["unit"] == "messages/s"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["value"] == d["value"]
+    # the reference arm is quoted on OUR arm's config (the same dictionary for the same launch); its bounded per-step sample is separate
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(1, 65536, 16384, 5, 28, "cuda-core")
+    assert d["sample"]["messages_per_step"] == 2 and d["sample"]["host_threads"] == d["cpu_baseline"]["cores"]
 
 
 def test_traffic_lookup_reads_profiles_and_reports_absence():
