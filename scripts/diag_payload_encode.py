@@ -1,3 +1,5 @@
+"""Timing breakdown of encode_pertinent_payloads at D = 65 536 (weights from the seed, payload upload, kernel) on a synthetic
+pertinency vector: used to tell first-call allocation cost from steady state."""
 import sys, time, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "scripts"))
 import numpy as np, torch
