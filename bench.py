@@ -677,7 +677,7 @@ def main():
     ap.add_argument("--config", default="board65536", choices=["board65536", "pack4096"])
     ap.add_argument("--messages-per-step", type=int, default=None, help="slice mode: messages per rank per step (weak scaling); default = the whole board / N")
     ap.add_argument("--chunk", type=int, default=CHUNK, help="messages per detect launch; the partial digests of the chunks are folded into a running digest")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
