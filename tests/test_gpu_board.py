@@ -97,6 +97,12 @@ def test_batch_invariance_and_ragged_sizes(detector, board):
         assert np.array_equal(got, base[lo:hi]), (lo, hi)
     empty = detector.detect((a[:0], b[:0]))
     assert len(empty) == 0
+    # one call that crosses the library's internal chunk (16 384 messages) by a ragged tail, throughput shapes with partial last CTAs
+    # (7 * 16 395 rotations is not a multiple of 6), against the same messages detected in two uneven calls
+    n = 16384 + 11
+    whole = detector.detect((a[:n], b[:n])).tensor
+    first, second = detector.detect((a[:5000], b[:5000])).tensor, detector.detect((a[5000:n], b[5000:n]), index0=5000).tensor
+    assert torch.equal(whole[:5000], first) and torch.equal(whole[5000:], second)
 
 
 def test_host_buffer_api_matches_device_api(detector, board):
